@@ -1,0 +1,272 @@
+"""Host-side mirror of the reference's interface for the BIH hot path, on top of libbihrt.so.
+
+The reference exposes the path through three C++ classes; this module keeps their names and the
+meaning of their entry points so that tests read like calls into the reference:
+
+    App::LoadModels(path)                R/src/App.cpp:65-167      -> Renderer.load_models(tri9 | path)
+    Renderer::Render(GPUArrayManager&)   R/src/Renderer.cpp:415-672 -> Renderer.build() + Renderer.render(...)
+    GPUArrayManager getters              R/src/GPUArrayManager.h:18-38 -> Renderer.reference_view()
+    Launch_cudaRender / TraverseTree     R/src/CUDAKernels.cu:227-447 -> Renderer.trace(rays)
+    m_cudaDestResource                   R/src/Renderer.h:46       -> Renderer.framebuffer()
+
+Everything goes through the C ABI in include/bihrt.h (ctypes); torch is used only for device
+buffers, streams and torch.distributed.  There is no CPU fallback: importing works anywhere, but
+constructing a Renderer without libbihrt.so or without a B200-class GPU raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(_PKG, "libbihrt.so")
+
+OK = 0
+RENDER_JITTER = 1
+
+
+class BihrtError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("bihrt error %d: %s" % (code, msg))
+        self.code = code
+
+
+class Config(C.Structure):
+    _fields_ = [("device", C.c_int32), ("flags", C.c_uint32), ("reserved", C.c_int32 * 6)]
+
+
+class Camera(C.Structure):
+    _fields_ = [("origin", C.c_float * 3), ("lower_left", C.c_float * 3),
+                ("horizontal", C.c_float * 3), ("vertical", C.c_float * 3)]
+
+    @staticmethod
+    def from_array(cam12):
+        cam12 = np.asarray(cam12, np.float32).reshape(12)
+        c = Camera()
+        C.memmove(C.byref(c), cam12.ctypes.data, 48)
+        return c
+
+
+class RefView(C.Structure):
+    _fields_ = [("n", C.c_int64), ("nu", C.c_int64), ("scene_lo", C.c_float * 3), ("scene_hi", C.c_float * 3),
+                ("morton_codes", C.c_void_p), ("tris_indexes", C.c_void_p), ("unique_morton_codes", C.c_void_p),
+                ("duplicates_cnts", C.c_void_p), ("first_idxs", C.c_void_p), ("clip_planes", C.c_void_p),
+                ("axis", C.c_void_p), ("is_leaf", C.c_void_p), ("children", C.c_void_p), ("parent", C.c_void_p),
+                ("leaf_parents", C.c_void_p)]
+
+
+class BuildInfo(C.Structure):
+    _fields_ = [("n", C.c_int64), ("nu", C.c_int64), ("node_bytes", C.c_int64), ("tri_bytes", C.c_int64),
+                ("last_build_ms", C.c_float), ("sort_passes", C.c_int32), ("reserved", C.c_int32 * 6)]
+
+
+# every symbol include/bihrt.h declares (tests check that the library exports all of them)
+ABI_SYMBOLS = [
+    "bihrt_version", "bihrt_create", "bihrt_destroy", "bihrt_last_error", "bihrt_set_stream", "bihrt_sync",
+    "bihrt_set_option", "bihrt_scene_load_triangles", "bihrt_scene_update_vertices", "bihrt_scene_load_obj",
+    "bihrt_build", "bihrt_get_build_info", "bihrt_export_reference_view", "bihrt_trace", "bihrt_trace_counted",
+    "bihrt_render", "bihrt_render_shard", "bihrt_render_hits", "bihrt_framebuffer", "bihrt_framebuffer_read",
+    "bihrt_bih_blob_bytes", "bihrt_bih_export", "bihrt_bih_import",
+]
+
+_lib = None
+
+
+def load_library(path=None):
+    """dlopen libbihrt.so (no CUDA call is made).  Raises if the library has not been built."""
+    global _lib
+    if _lib is None or path:
+        p = path or LIB_PATH
+        if not os.path.exists(p):
+            raise BihrtError(-100, "%s not found: build it with `make -C %s` (there is no CPU fallback)" % (p, _PKG))
+        lib = C.CDLL(p)
+        lib.bihrt_last_error.restype = C.c_char_p
+        lib.bihrt_last_error.argtypes = [C.c_void_p]
+        lib.bihrt_destroy.restype = None
+        lib.bihrt_destroy.argtypes = [C.c_void_p]
+        _lib = lib
+    return _lib
+
+
+def _ptr(x):
+    """Pointer of a numpy array (host), a torch tensor (host or device), an int address, or None."""
+    if x is None:
+        return None
+    if isinstance(x, np.ndarray):
+        return C.c_void_p(x.ctypes.data)
+    if isinstance(x, int):
+        return C.c_void_p(x)
+    if hasattr(x, "data_ptr"):
+        return C.c_void_p(x.data_ptr())
+    raise TypeError("unsupported buffer type %r" % type(x))
+
+
+class Renderer:
+    """One context = one GPU.  Mirrors the call order of the reference's frame:
+    load_models -> build -> render/trace -> framebuffer."""
+
+    def __init__(self, device=0, stream=None):
+        self._lib = load_library()
+        self._ctx = C.c_void_p()
+        cfg = Config(device=device, flags=0)
+        rc = self._lib.bihrt_create(C.byref(self._ctx), C.byref(cfg))
+        if rc != OK:
+            self._ctx = C.c_void_p()
+            raise BihrtError(rc, "bihrt_create failed (no sm_100-class GPU visible? there is no CPU fallback)")
+        self.device = device
+        self.n = 0
+        if stream is not None:
+            self.set_stream(stream)
+
+    # -- plumbing -----------------------------------------------------------------------------
+    def _check(self, rc):
+        if rc != OK:
+            raise BihrtError(rc, self._lib.bihrt_last_error(self._ctx).decode())
+
+    def close(self):
+        if getattr(self, "_ctx", None) and self._ctx.value:
+            self._lib.bihrt_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream):
+        """Run on a caller-owned stream (int handle, e.g. torch.cuda.current_stream().cuda_stream)."""
+        self._check(self._lib.bihrt_set_stream(self._ctx, C.c_void_p(int(cuda_stream) if cuda_stream else 0)))
+
+    def sync(self):
+        self._check(self._lib.bihrt_sync(self._ctx))
+
+    def set_option(self, name, value):
+        self._check(self._lib.bihrt_set_option(self._ctx, name.encode(), C.c_int64(int(value))))
+
+    # -- App::LoadModels ------------------------------------------------------------------------
+    def load_models(self, src):
+        """src: path of a Wavefront .obj, or (N,9) float32 triangles (numpy / torch, host or device)."""
+        if isinstance(src, (str, bytes, os.PathLike)):
+            self._check(self._lib.bihrt_scene_load_obj(self._ctx, os.fsencode(src)))
+            self.n = None
+            return self
+        if isinstance(src, np.ndarray):
+            src = np.ascontiguousarray(src, dtype=np.float32)
+            n = src.size // 9
+        else:
+            n = src.numel() // 9
+        self._keep = src
+        self._check(self._lib.bihrt_scene_load_triangles(self._ctx, _ptr(src), C.c_int64(n)))
+        self.n = n
+        return self
+
+    def update_vertices(self, src):
+        if isinstance(src, np.ndarray):
+            src = np.ascontiguousarray(src, dtype=np.float32)
+            n = src.size // 9
+        else:
+            n = src.numel() // 9
+        self._keep = src
+        self._check(self._lib.bihrt_scene_update_vertices(self._ctx, _ptr(src), C.c_int64(n)))
+
+    # -- first half of Renderer::Render -----------------------------------------------------------
+    def build(self):
+        self._check(self._lib.bihrt_build(self._ctx))
+        return self
+
+    def build_info(self):
+        bi = BuildInfo()
+        self._check(self._lib.bihrt_get_build_info(self._ctx, C.byref(bi)))
+        return {"n": bi.n, "nu": bi.nu, "node_bytes": bi.node_bytes, "tri_bytes": bi.tri_bytes,
+                "last_build_ms": bi.last_build_ms, "sort_passes": bi.sort_passes}
+
+    def reference_view(self):
+        """The reference's device arrays as numpy arrays, trimmed to n / Nu."""
+        info = self.build_info()
+        n, m = info["n"], max(info["n"], 1)
+        out = {
+            "morton_codes": np.zeros(m, np.uint32), "tris_indexes": np.zeros(m, np.uint32),
+            "unique_morton_codes": np.zeros(m, np.uint32), "duplicates_cnts": np.zeros(m, np.uint32),
+            "first_idxs": np.zeros(m, np.int32), "clip_planes": np.zeros((m, 2), np.float32),
+            "axis": np.zeros(m, np.int32), "is_leaf": np.zeros((m, 2), np.uint8),
+            "children": np.zeros((m, 2), np.int32), "parent": np.zeros(m, np.int32),
+            "leaf_parents": np.zeros(m, np.int32)}
+        v = RefView()
+        for k, a in out.items():
+            setattr(v, k, a.ctypes.data)
+        self._check(self._lib.bihrt_export_reference_view(self._ctx, C.byref(v)))
+        nu, ni = v.nu, max(v.nu - 1, 0)
+        trim = {"morton_codes": n, "tris_indexes": n, "unique_morton_codes": nu, "duplicates_cnts": nu,
+                "first_idxs": nu, "leaf_parents": nu, "clip_planes": ni, "axis": ni, "is_leaf": ni,
+                "children": ni, "parent": ni}
+        res = {k: out[k][:trim[k]] for k in out}
+        res.update(n=n, nu=nu, scene_lo=np.array(list(v.scene_lo), np.float32),
+                   scene_hi=np.array(list(v.scene_hi), np.float32))
+        return res
+
+    # -- Launch_cudaRender / TraverseTree -----------------------------------------------------------
+    def trace(self, rays, t=None, slot=None, prim=None, counted=False):
+        """rays: (N,6) float32 o.xyz d.xyz (numpy or torch, host or device).  With numpy input the
+        outputs are numpy arrays; with torch input they are torch tensors on the rays' device unless
+        given.  Returns (t, slot, prim[, counters])."""
+        if isinstance(rays, np.ndarray):
+            rays = np.ascontiguousarray(rays, dtype=np.float32)
+            n = rays.size // 6
+            t = np.empty(n, np.float32) if t is None else t
+            slot = np.empty(n, np.int32) if slot is None else slot
+            prim = np.empty(n, np.int32) if prim is None else prim
+        else:
+            import torch
+            n = rays.numel() // 6
+            t = torch.empty(n, dtype=torch.float32, device=rays.device) if t is None else t
+            slot = torch.empty(n, dtype=torch.int32, device=rays.device) if slot is None else slot
+            prim = torch.empty(n, dtype=torch.int32, device=rays.device) if prim is None else prim
+        if counted:
+            cnt = (C.c_uint64 * 4)()
+            self._check(self._lib.bihrt_trace_counted(self._ctx, _ptr(rays), C.c_int64(n), _ptr(t), _ptr(slot), _ptr(prim), cnt))
+            return t, slot, prim, {"nodes": cnt[0], "tris": cnt[1], "max_stack": cnt[2], "rays": cnt[3]}
+        self._check(self._lib.bihrt_trace(self._ctx, _ptr(rays), C.c_int64(n), _ptr(t), _ptr(slot), _ptr(prim)))
+        return t, slot, prim
+
+    def render(self, camera, w, h, spp=1, seed=1984, jitter=False, shard=(0, 1)):
+        cam = camera if isinstance(camera, Camera) else Camera.from_array(camera)
+        self._check(self._lib.bihrt_render_shard(self._ctx, C.byref(cam), C.c_int32(w), C.c_int32(h), C.c_int32(spp),
+                                                 C.c_uint64(seed), C.c_uint32(RENDER_JITTER if jitter else 0),
+                                                 C.c_int32(shard[0]), C.c_int32(shard[1])))
+        return self
+
+    def render_hits(self, camera, w, h, spp=1, seed=1984, jitter=False):
+        cam = camera if isinstance(camera, Camera) else Camera.from_array(camera)
+        n = w * h * spp
+        t, slot, prim = np.empty(n, np.float32), np.empty(n, np.int32), np.empty(n, np.int32)
+        self._check(self._lib.bihrt_render_hits(self._ctx, C.byref(cam), C.c_int32(w), C.c_int32(h), C.c_int32(spp),
+                                                C.c_uint64(seed), C.c_uint32(RENDER_JITTER if jitter else 0),
+                                                _ptr(t), _ptr(slot), _ptr(prim)))
+        return t, slot, prim
+
+    # -- m_cudaDestResource ---------------------------------------------------------------------------
+    def framebuffer_ptr(self):
+        p, w, h = C.c_void_p(), C.c_int32(), C.c_int32()
+        self._check(self._lib.bihrt_framebuffer(self._ctx, C.byref(p), C.byref(w), C.byref(h)))
+        return p.value, w.value, h.value
+
+    def framebuffer(self, out=None):
+        """Packed r | g<<8 | b<<16 pixels, row 0 = bottom, as a (h, w) uint32 host array."""
+        _, w, h = self.framebuffer_ptr()
+        if out is None:
+            out = np.empty((h, w), np.uint32)
+        self._check(self._lib.bihrt_framebuffer_read(self._ctx, _ptr(out)))
+        return out
+
+    # -- BIH replication ---------------------------------------------------------------------------
+    def bih_blob_bytes(self):
+        b = C.c_uint64()
+        self._check(self._lib.bihrt_bih_blob_bytes(self._ctx, C.byref(b)))
+        return b.value
+
+    def bih_export(self, dev_buffer, nbytes):
+        self._check(self._lib.bihrt_bih_export(self._ctx, _ptr(dev_buffer), C.c_uint64(nbytes)))
+
+    def bih_import(self, dev_buffer, nbytes):
+        self._check(self._lib.bihrt_bih_import(self._ctx, _ptr(dev_buffer), C.c_uint64(nbytes)))

@@ -1,0 +1,502 @@
+// C ABI of libbihrt.so (include/bihrt.h): context, scene load, build, export, trace, framebuffer.
+// Host side of the path: replaces App::LoadModels (R/src/App.cpp:65-167), GPUArrayManager
+// (R/src/GPUArrayManager.cpp) and the launch half of Renderer (R/src/Renderer.cpp:415-503,638-640).
+#include "bihrt_internal.cuh"
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+int bihrt_fail(bihrt_ctx* c, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf;
+    return code;
+}
+
+#define ENTER(c) do { if (!(c)) return BIHRT_ERR_INVALID; BIHRT_CUDA((c), cudaSetDevice((c)->device)); } while (0)
+
+static bool is_device_ptr(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+template <typename T>
+static int dev_alloc(bihrt_ctx* c, T** p, size_t count) {
+    if (*p) { cudaFree(*p); *p = nullptr; }
+    if (count == 0) count = 1;
+    cudaError_t e = cudaMalloc((void**)p, count * sizeof(T));
+    if (e != cudaSuccess) { *p = nullptr; cudaGetLastError(); return bihrt_fail(c, BIHRT_ERR_NOMEM, "cudaMalloc(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(e)); }
+    return BIHRT_OK;
+}
+template <typename T>
+static void dev_free(T** p) { if (*p) { cudaFree(*p); *p = nullptr; } }
+
+template <typename T>
+static int fetch(bihrt_ctx* c, std::vector<T>& dst, const T* src, size_t count) {
+    dst.resize(count);
+    if (count) BIHRT_CUDA(c, cudaMemcpyAsync(dst.data(), src, count * sizeof(T), cudaMemcpyDeviceToHost, c->stream));
+    return BIHRT_OK;
+}
+
+static size_t lookback_words_for(int64_t n) {
+    // must match build.cu: 4 onesweep passes x tiles(4096) x 256 + rle tiles(2048)
+    size_t os_tiles = (size_t)((n + 4095) / 4096), rle_tiles = (size_t)((n + 2047) / 2048);
+    return 4 * os_tiles * 256 + rle_tiles + 16;
+}
+
+static size_t blob_capacity(int64_t n) { return 64 + (size_t)n * 16 + (size_t)n * 48 + 64; }
+
+static void bind_blob(bihrt_ctx* c, int64_t cap) {
+    c->d_hdr = reinterpret_cast<BihHeader*>(c->d_blob);
+    c->d_nodes = reinterpret_cast<BihNode*>(c->d_blob + 64);
+    c->d_tris = reinterpret_cast<BihTri*>(c->d_blob + 64 + (size_t)cap * 16);
+}
+
+// GPUArrayManager::AllocateTris / AllocateMortonCodes / AllocateBIHTree (R/src/GPUArrayManager.cpp:7-91)
+static int ensure_capacity(bihrt_ctx* c, int64_t n, bool with_build_scratch) {
+    int rc;
+    if (n > c->cap_n || !c->d_blob) {
+        int64_t cap = std::max<int64_t>(n, 1);
+        if ((rc = dev_alloc(c, &c->d_blob, blob_capacity(cap)))) return rc;
+        c->blob_cap = blob_capacity(cap);
+        dev_free(&c->d_tri_in);
+        for (int i = 0; i < 2; i++) { dev_free(&c->d_keys[i]); dev_free(&c->d_vals[i]); }
+        dev_free(&c->d_umc); dev_free(&c->d_first); dev_free(&c->d_lookback); dev_free(&c->d_arrive); dev_free(&c->d_boxscratch);
+        c->cap_n = cap;
+        c->have_scene = false; c->built = false;
+        bind_blob(c, cap);
+    }
+    if (with_build_scratch && !c->d_keys[0]) {
+        int64_t cap = c->cap_n;
+        if ((rc = dev_alloc(c, &c->d_tri_in, (size_t)cap * 9 + 4))) return rc;
+        for (int i = 0; i < 2; i++) {
+            if ((rc = dev_alloc(c, &c->d_keys[i], (size_t)cap + 8))) return rc;
+            if ((rc = dev_alloc(c, &c->d_vals[i], (size_t)cap + 8))) return rc;
+        }
+        if ((rc = dev_alloc(c, &c->d_umc, (size_t)cap + 8))) return rc;
+        if ((rc = dev_alloc(c, &c->d_first, (size_t)cap + 8))) return rc;
+        c->lookback_words = lookback_words_for(cap);
+        if ((rc = dev_alloc(c, &c->d_lookback, c->lookback_words))) return rc;
+        if ((rc = dev_alloc(c, &c->d_arrive, (size_t)cap + 8))) return rc;
+        if ((rc = dev_alloc(c, &c->d_boxscratch, (size_t)cap * 16 + 16))) return rc;
+    }
+    return BIHRT_OK;
+}
+
+extern "C" {
+
+int bihrt_version(void) { return BIHRT_VERSION; }
+
+int bihrt_create(bihrt_ctx** out, const bihrt_config* cfg) {
+    if (!out) return BIHRT_ERR_INVALID;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return BIHRT_ERR_CUDA; }   // no CPU fallback
+    bihrt_ctx* c = new (std::nothrow) bihrt_ctx();
+    if (!c) return BIHRT_ERR_NOMEM;
+    c->device = cfg ? cfg->device : 0;
+    if (c->device < 0 || c->device >= ndev) { delete c; return BIHRT_ERR_INVALID; }
+    cudaDeviceProp prop;
+    if (cudaSetDevice(c->device) != cudaSuccess || cudaGetDeviceProperties(&prop, c->device) != cudaSuccess) { delete c; return BIHRT_ERR_CUDA; }
+    if (prop.major < 10) { delete c; return BIHRT_ERR_CUDA; }   // sm_100a code only
+    c->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return BIHRT_ERR_CUDA; }
+    c->stream = c->own_stream;
+    cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1);
+    int rc = 0;
+    rc |= dev_alloc(c, &c->d_hist, 2048);
+    rc |= dev_alloc(c, &c->d_scenebox_enc, 8);
+    rc |= dev_alloc(c, &c->d_counters, 8);
+    rc |= dev_alloc(c, &c->d_work, 4);
+    if (rc) { bihrt_destroy(c); return BIHRT_ERR_NOMEM; }
+    *out = c;
+    return BIHRT_OK;
+}
+
+void bihrt_destroy(bihrt_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    dev_free(&c->d_tri_in); dev_free(&c->d_blob);
+    for (int i = 0; i < 2; i++) { dev_free(&c->d_keys[i]); dev_free(&c->d_vals[i]); }
+    dev_free(&c->d_umc); dev_free(&c->d_first); dev_free(&c->d_hist); dev_free(&c->d_lookback);
+    dev_free(&c->d_arrive); dev_free(&c->d_boxscratch); dev_free(&c->d_scenebox_enc);
+    dev_free(&c->d_fb); dev_free(&c->d_counters); dev_free(&c->d_work);
+    if (c->d_io) { cudaFree(c->d_io); c->d_io = nullptr; }
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+const char* bihrt_last_error(const bihrt_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+int bihrt_set_stream(bihrt_ctx* c, void* s) {
+    ENTER(c);
+    BIHRT_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    return BIHRT_OK;
+}
+
+int bihrt_sync(bihrt_ctx* c) {
+    ENTER(c);
+    BIHRT_CUDA(c, cudaStreamSynchronize(c->stream));
+    return BIHRT_OK;
+}
+
+int bihrt_set_option(bihrt_ctx* c, const char* name, int64_t v) {
+    if (!c || !name) return BIHRT_ERR_INVALID;
+    if (!strcmp(name, "trace_blocks_per_sm")) c->opt_trace_blocks_per_sm = (int)v;
+    else if (!strcmp(name, "trace_variant")) c->opt_trace_variant = (int)v;
+    else return bihrt_fail(c, BIHRT_ERR_INVALID, "unknown option '%s'", name);
+    return BIHRT_OK;
+}
+
+// ---- scene load ------------------------------------------------------------------------------
+static int upload_triangles(bihrt_ctx* c, const float* xyz9, int64_t n) {
+    if (n > 0) {
+        cudaMemcpyKind kind = is_device_ptr(xyz9) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+        BIHRT_CUDA(c, cudaMemcpyAsync(c->d_tri_in, xyz9, (size_t)n * 36, kind, c->stream));
+    }
+    return BIHRT_OK;
+}
+
+int bihrt_scene_load_triangles(bihrt_ctx* c, const float* xyz9, int64_t n) {
+    ENTER(c);
+    if (n < 0 || (n > 0 && !xyz9)) return bihrt_fail(c, BIHRT_ERR_INVALID, "bad triangle array");
+    if (n >= (1ll << 30)) return bihrt_fail(c, BIHRT_ERR_INVALID, "at most 2^30-1 triangles (30-bit child references)");
+    int rc = ensure_capacity(c, n, true);
+    if (rc) return rc;
+    c->n = n; c->have_scene = true; c->built = false;
+    return upload_triangles(c, xyz9, n);
+}
+
+int bihrt_scene_update_vertices(bihrt_ctx* c, const float* xyz9, int64_t n) {
+    ENTER(c);
+    if (!c->have_scene || !c->d_tri_in) return bihrt_fail(c, BIHRT_ERR_STATE, "no scene loaded");
+    if (n != c->n) return bihrt_fail(c, BIHRT_ERR_INVALID, "update must keep the triangle count (%lld != %lld)", (long long)n, (long long)c->n);
+    c->built = false;
+    return upload_triangles(c, xyz9, n);
+}
+
+// Minimal Wavefront OBJ reader: `v x y z` and `f a b c ...` (a, a/b, a/b/c, a//c; negative = relative),
+// polygons fan-triangulated in face order.  Replaces Model(path) -> Assimp (R/src/Model.cpp:10-29);
+// Assimp's own triangulation order is not reproducible here (binary-only dependency; parity unpinned).
+int bihrt_scene_load_obj(bihrt_ctx* c, const char* path) {
+    ENTER(c);
+    if (!path) return BIHRT_ERR_INVALID;
+    FILE* f = fopen(path, "r");
+    if (!f) return bihrt_fail(c, BIHRT_ERR_IO, "cannot open '%s'", path);
+    std::vector<float> verts, tris;
+    std::vector<long> poly;
+    char line[4096];
+    int rc = BIHRT_OK;
+    while (fgets(line, sizeof line, f)) {
+        if (line[0] == 'v' && (line[1] == ' ' || line[1] == '\t')) {
+            float x, y, z;
+            if (sscanf(line + 2, "%f %f %f", &x, &y, &z) != 3) { rc = bihrt_fail(c, BIHRT_ERR_IO, "bad vertex line in '%s'", path); break; }
+            verts.push_back(x); verts.push_back(y); verts.push_back(z);
+        } else if (line[0] == 'f' && (line[1] == ' ' || line[1] == '\t')) {
+            poly.clear();
+            char* p = line + 2;
+            for (;;) {
+                while (*p == ' ' || *p == '\t') p++;
+                if (*p == 0 || *p == '\n' || *p == '\r' || *p == '#') break;
+                char* end;
+                long idx = strtol(p, &end, 10);
+                if (end == p) { rc = bihrt_fail(c, BIHRT_ERR_IO, "bad face line in '%s'", path); break; }
+                long nv = (long)(verts.size() / 3);
+                idx = idx < 0 ? nv + idx : idx - 1;
+                if (idx < 0 || idx >= nv) { rc = bihrt_fail(c, BIHRT_ERR_IO, "face index out of range in '%s'", path); break; }
+                poly.push_back(idx);
+                p = end;
+                while (*p && *p != ' ' && *p != '\t' && *p != '\n' && *p != '\r') p++;   // skip /vt/vn
+            }
+            if (rc) break;
+            for (size_t k = 1; k + 1 < poly.size(); k++) {
+                const long id[3] = { poly[0], poly[k], poly[k + 1] };
+                for (int v = 0; v < 3; v++) for (int a = 0; a < 3; a++) tris.push_back(verts[3 * id[v] + a]);
+            }
+        }
+    }
+    fclose(f);
+    if (rc) return rc;
+    return bihrt_scene_load_triangles(c, tris.data(), (int64_t)(tris.size() / 9));
+}
+
+// ---- build -------------------------------------------------------------------------------------
+int bihrt_build(bihrt_ctx* c) {
+    ENTER(c);
+    if (!c->have_scene || !c->d_tri_in) return bihrt_fail(c, BIHRT_ERR_STATE, "no scene loaded");
+    BIHRT_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+    if (c->n == 0) {
+        BIHRT_CUDA(c, cudaMemsetAsync(c->d_hdr, 0, sizeof(BihHeader), c->stream));
+    } else {
+        int rc = bihrt_build_launch(c);
+        if (rc) return rc;
+    }
+    BIHRT_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+    c->built = true; c->build_timed = true;
+    return BIHRT_OK;
+}
+
+static int fetch_header(bihrt_ctx* c, BihHeader* h) {
+    BIHRT_CUDA(c, cudaMemcpyAsync(h, c->d_hdr, sizeof(BihHeader), cudaMemcpyDeviceToHost, c->stream));
+    BIHRT_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (h->status) return bihrt_fail(c, BIHRT_ERR_INTERNAL, "device watchdog tripped during build (status %u)", h->status);
+    return BIHRT_OK;
+}
+
+int bihrt_get_build_info(bihrt_ctx* c, bihrt_build_info* out) {
+    ENTER(c);
+    if (!out) return BIHRT_ERR_INVALID;
+    if (!c->built) return bihrt_fail(c, BIHRT_ERR_STATE, "BIH not built");
+    BihHeader h;
+    int rc = fetch_header(c, &h);
+    if (rc) return rc;
+    memset(out, 0, sizeof *out);
+    out->n = h.n; out->nu = h.nu;
+    out->node_bytes = h.nu > 1 ? (int64_t)(h.nu - 1) * 16 : 0;
+    out->tri_bytes = (int64_t)h.n * 48;
+    out->sort_passes = 4;
+    if (c->build_timed) { float ms = 0; if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) out->last_build_ms = ms; else cudaGetLastError(); }
+    return BIHRT_OK;
+}
+
+int bihrt_export_reference_view(bihrt_ctx* c, bihrt_refview* v) {
+    ENTER(c);
+    if (!v) return BIHRT_ERR_INVALID;
+    if (!c->built || !c->d_keys[0]) return bihrt_fail(c, BIHRT_ERR_STATE, "reference view needs a BIH built on this context");
+    BihHeader h;
+    int rc = fetch_header(c, &h);
+    if (rc) return rc;
+    const size_t n = h.n, nu = h.nu, ni = nu > 1 ? nu - 1 : 0;
+    v->n = (int64_t)n; v->nu = (int64_t)nu;
+    for (int k = 0; k < 3; k++) { v->scene_lo[k] = h.lo[k]; v->scene_hi[k] = h.hi[k]; }
+    if (n == 0) return BIHRT_OK;
+    std::vector<uint32_t> first, umc;
+    std::vector<BihNode> nodes;
+    if ((rc = fetch(c, first, c->d_first, nu + 1))) return rc;
+    if ((rc = fetch(c, nodes, c->d_nodes, ni))) return rc;
+    if (v->morton_codes) BIHRT_CUDA(c, cudaMemcpyAsync(v->morton_codes, c->d_keys[0], n * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (v->tris_indexes) BIHRT_CUDA(c, cudaMemcpyAsync(v->tris_indexes, c->d_vals[0], n * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (v->unique_morton_codes) BIHRT_CUDA(c, cudaMemcpyAsync(v->unique_morton_codes, c->d_umc, nu * 4, cudaMemcpyDeviceToHost, c->stream));
+    BIHRT_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (size_t k = 0; k < nu; k++) {
+        if (v->first_idxs) v->first_idxs[k] = (int32_t)first[k];
+        if (v->duplicates_cnts) v->duplicates_cnts[k] = first[k + 1] - first[k];
+        if (v->leaf_parents) v->leaf_parents[k] = -1;
+    }
+    for (size_t i = 0; i < ni; i++) if (v->parent) v->parent[i] = -1;
+    for (size_t i = 0; i < ni; i++) {
+        const BihNode& nd = nodes[i];
+        const bool ll = nd.ref_l & BIH_REF_LEAF, rl = nd.ref_r & BIH_REF_LEAF;
+        const uint32_t il = nd.ref_l & BIH_REF_INDEX, ir = nd.ref_r & BIH_REF_INDEX;
+        uint32_t split;
+        if (!ll) split = il;
+        else if (!rl) split = ir - 1;
+        else split = (uint32_t)(std::lower_bound(first.begin(), first.begin() + nu, il) - first.begin());   // leaf whose first slot is il
+        if (v->clip_planes) { v->clip_planes[2 * i] = nd.clip0; v->clip_planes[2 * i + 1] = nd.clip1; }
+        if (v->axis) v->axis[i] = (int32_t)(((nd.ref_l >> 30) & 1u) | ((nd.ref_r >> 29) & 2u));
+        if (v->is_leaf) { v->is_leaf[2 * i] = ll; v->is_leaf[2 * i + 1] = rl; }
+        if (v->children) { v->children[2 * i] = (int32_t)split; v->children[2 * i + 1] = (int32_t)split + 1; }
+        if (ll) { if (v->leaf_parents) v->leaf_parents[split] = (int32_t)i; } else if (v->parent) v->parent[split] = (int32_t)i;
+        if (rl) { if (v->leaf_parents) v->leaf_parents[split + 1] = (int32_t)i; } else if (v->parent) v->parent[split + 1] = (int32_t)i;
+    }
+    return BIHRT_OK;
+}
+
+// ---- trace -------------------------------------------------------------------------------------
+static int ensure_io(bihrt_ctx* c, size_t bytes) {
+    if (bytes <= c->io_cap) return BIHRT_OK;
+    if (c->d_io) { cudaFree(c->d_io); c->d_io = nullptr; c->io_cap = 0; }
+    cudaError_t e = cudaMalloc(&c->d_io, bytes);
+    if (e != cudaSuccess) { cudaGetLastError(); return bihrt_fail(c, BIHRT_ERR_NOMEM, "cudaMalloc(%zu) for ray staging failed", bytes); }
+    c->io_cap = bytes;
+    return BIHRT_OK;
+}
+
+static void base_args(bihrt_ctx* c, TraceArgs& a) {
+    memset(&a, 0, sizeof a);
+    a.hdr = c->d_hdr; a.nodes = c->d_nodes; a.tris = c->d_tris;
+    a.counters = c->d_counters; a.work = c->d_work;
+    a.shard_index = 0; a.shard_count = 1;
+}
+
+// outputs may individually be host or device; host ones are staged through d_io
+struct OutStage { float* t; int32_t* slot; int32_t* prim; float* ht; int32_t* hslot; int32_t* hprim; };
+
+static int stage_outputs(bihrt_ctx* c, int64_t n, size_t front_bytes, float* t, int32_t* slot, int32_t* prim, OutStage& o, uint8_t** front) {
+    const bool dt = t && !is_device_ptr(t), ds = slot && !is_device_ptr(slot), dp = prim && !is_device_ptr(prim);
+    size_t need = front_bytes + ((dt ? 1 : 0) + (ds ? 1 : 0) + (dp ? 1 : 0)) * (size_t)n * 4 + 256;
+    int rc = ensure_io(c, need);
+    if (rc) return rc;
+    uint8_t* p = (uint8_t*)c->d_io;
+    *front = p;
+    p += (front_bytes + 255) / 256 * 256;
+    o = OutStage{ t, slot, prim, nullptr, nullptr, nullptr };
+    if (dt) { o.ht = t; o.t = (float*)p; p += (size_t)n * 4; }
+    if (ds) { o.hslot = slot; o.slot = (int32_t*)p; p += (size_t)n * 4; }
+    if (dp) { o.hprim = prim; o.prim = (int32_t*)p; p += (size_t)n * 4; }
+    return BIHRT_OK;
+}
+
+static int unstage_outputs(bihrt_ctx* c, int64_t n, const OutStage& o) {
+    bool any = false;
+    if (o.ht) { BIHRT_CUDA(c, cudaMemcpyAsync(o.ht, o.t, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream)); any = true; }
+    if (o.hslot) { BIHRT_CUDA(c, cudaMemcpyAsync(o.hslot, o.slot, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream)); any = true; }
+    if (o.hprim) { BIHRT_CUDA(c, cudaMemcpyAsync(o.hprim, o.prim, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream)); any = true; }
+    if (any) BIHRT_CUDA(c, cudaStreamSynchronize(c->stream));
+    return BIHRT_OK;
+}
+
+static int trace_impl(bihrt_ctx* c, const bihrt_ray* rays, int64_t n, float* t, int32_t* slot, int32_t* prim, uint64_t* counters) {
+    ENTER(c);
+    if (!c->built) return bihrt_fail(c, BIHRT_ERR_STATE, "BIH not built");
+    if (n < 0 || (n > 0 && !rays)) return bihrt_fail(c, BIHRT_ERR_INVALID, "bad ray array");
+    if (n >= (1ll << 36)) return bihrt_fail(c, BIHRT_ERR_INVALID, "too many rays in one call");
+    if (counters) BIHRT_CUDA(c, cudaMemsetAsync(c->d_counters, 0, 32, c->stream));
+    if (n > 0) {
+        const bool rays_dev = is_device_ptr(rays);
+        OutStage o; uint8_t* front;
+        int rc = stage_outputs(c, n, rays_dev ? 0 : (size_t)n * sizeof(bihrt_ray), t, slot, prim, o, &front);
+        if (rc) return rc;
+        TraceArgs a; base_args(c, a);
+        if (rays_dev) a.rays = rays;
+        else { BIHRT_CUDA(c, cudaMemcpyAsync(front, rays, (size_t)n * sizeof(bihrt_ray), cudaMemcpyHostToDevice, c->stream)); a.rays = (const bihrt_ray*)front; }
+        a.nrays = n; a.out_t = o.t; a.out_slot = o.slot; a.out_prim = o.prim;
+        if ((rc = bihrt_trace_launch(c, a, 0, counters != nullptr))) return rc;
+        if ((rc = unstage_outputs(c, n, o))) return rc;
+    }
+    if (counters) {
+        unsigned long long h[4];
+        BIHRT_CUDA(c, cudaMemcpyAsync(h, c->d_counters, 32, cudaMemcpyDeviceToHost, c->stream));
+        BIHRT_CUDA(c, cudaStreamSynchronize(c->stream));
+        counters[0] = h[0]; counters[1] = h[1]; counters[2] = h[2]; counters[3] = (uint64_t)n;
+    }
+    return BIHRT_OK;
+}
+
+int bihrt_trace(bihrt_ctx* c, const bihrt_ray* rays, int64_t n, float* t, int32_t* slot, int32_t* prim) {
+    return trace_impl(c, rays, n, t, slot, prim, nullptr);
+}
+int bihrt_trace_counted(bihrt_ctx* c, const bihrt_ray* rays, int64_t n, float* t, int32_t* slot, int32_t* prim, uint64_t counters[4]) {
+    if (!counters) return BIHRT_ERR_INVALID;
+    return trace_impl(c, rays, n, t, slot, prim, counters);
+}
+
+static int render_check(bihrt_ctx* c, const bihrt_camera* cam, int w, int h, int spp, int si, int sc) {
+    if (!c->built) return bihrt_fail(c, BIHRT_ERR_STATE, "BIH not built");
+    if (!cam || w <= 0 || h <= 0 || spp <= 0 || (int64_t)w * h >= (1ll << 31)) return bihrt_fail(c, BIHRT_ERR_INVALID, "bad render arguments");
+    if (sc < 1 || si < 0 || si >= sc) return bihrt_fail(c, BIHRT_ERR_INVALID, "bad shard %d of %d", si, sc);
+    return BIHRT_OK;
+}
+
+int bihrt_render_shard(bihrt_ctx* c, const bihrt_camera* cam, int32_t w, int32_t h, int32_t spp, uint64_t seed, uint32_t flags,
+                       int32_t shard_index, int32_t shard_count) {
+    ENTER(c);
+    int rc = render_check(c, cam, w, h, spp, shard_index, shard_count);
+    if (rc) return rc;
+    const size_t px = (size_t)w * h;
+    if (px > c->fb_cap) { if ((rc = dev_alloc(c, &c->d_fb, px))) { c->fb_cap = 0; return rc; } c->fb_cap = px; }   // CreateCUDABuffers, R/src/Renderer.cpp:762-768
+    c->fb_w = w; c->fb_h = h;
+    if (shard_count > 1) BIHRT_CUDA(c, cudaMemsetAsync(c->d_fb, 0, px * 4, c->stream));
+    TraceArgs a; base_args(c, a);
+    a.cam = *cam; a.w = w; a.h = h; a.spp = spp; a.seed = seed; a.flags = flags;
+    a.shard_index = shard_index; a.shard_count = shard_count; a.fb = c->d_fb;
+    return bihrt_trace_launch(c, a, 1, false);
+}
+
+int bihrt_render(bihrt_ctx* c, const bihrt_camera* cam, int32_t w, int32_t h, int32_t spp, uint64_t seed, uint32_t flags) {
+    return bihrt_render_shard(c, cam, w, h, spp, seed, flags, 0, 1);
+}
+
+int bihrt_render_hits(bihrt_ctx* c, const bihrt_camera* cam, int32_t w, int32_t h, int32_t spp, uint64_t seed, uint32_t flags,
+                      float* t, int32_t* slot, int32_t* prim) {
+    ENTER(c);
+    int rc = render_check(c, cam, w, h, spp, 0, 1);
+    if (rc) return rc;
+    const int64_t n = (int64_t)w * h * spp;
+    OutStage o; uint8_t* front;
+    if ((rc = stage_outputs(c, n, 0, t, slot, prim, o, &front))) return rc;
+    TraceArgs a; base_args(c, a);
+    a.cam = *cam; a.w = w; a.h = h; a.spp = spp; a.seed = seed; a.flags = flags;
+    a.out_t = o.t; a.out_slot = o.slot; a.out_prim = o.prim;
+    if ((rc = bihrt_trace_launch(c, a, 2, false))) return rc;
+    return unstage_outputs(c, n, o);
+}
+
+// ---- framebuffer -------------------------------------------------------------------------------
+int bihrt_framebuffer(bihrt_ctx* c, uint32_t** dev_ptr, int32_t* w, int32_t* h) {
+    if (!c) return BIHRT_ERR_INVALID;
+    if (!c->d_fb) return bihrt_fail(c, BIHRT_ERR_STATE, "nothing rendered yet");
+    if (dev_ptr) *dev_ptr = c->d_fb;
+    if (w) *w = c->fb_w;
+    if (h) *h = c->fb_h;
+    return BIHRT_OK;
+}
+
+int bihrt_framebuffer_read(bihrt_ctx* c, uint32_t* host_dst) {
+    ENTER(c);
+    if (!c->d_fb) return bihrt_fail(c, BIHRT_ERR_STATE, "nothing rendered yet");
+    if (!host_dst) return BIHRT_ERR_INVALID;
+    BIHRT_CUDA(c, cudaMemcpyAsync(host_dst, c->d_fb, (size_t)c->fb_w * c->fb_h * 4, cudaMemcpyDeviceToHost, c->stream));
+    BIHRT_CUDA(c, cudaStreamSynchronize(c->stream));
+    return BIHRT_OK;
+}
+
+// ---- BIH replication ----------------------------------------------------------------------------
+// blob = [BihHeader 64 B][nodes (nu-1) x 16 B][triangles n x 48 B]
+int bihrt_bih_blob_bytes(bihrt_ctx* c, uint64_t* bytes) {
+    ENTER(c);
+    if (!bytes) return BIHRT_ERR_INVALID;
+    if (!c->built) return bihrt_fail(c, BIHRT_ERR_STATE, "BIH not built");
+    BihHeader h;
+    int rc = fetch_header(c, &h);
+    if (rc) return rc;
+    *bytes = 64 + (uint64_t)(h.nu > 1 ? h.nu - 1 : 0) * 16 + (uint64_t)h.n * 48;
+    return BIHRT_OK;
+}
+
+int bihrt_bih_export(bihrt_ctx* c, void* dev_dst, uint64_t bytes) {
+    ENTER(c);
+    uint64_t need;
+    int rc = bihrt_bih_blob_bytes(c, &need);
+    if (rc) return rc;
+    if (!dev_dst || bytes < need) return bihrt_fail(c, BIHRT_ERR_INVALID, "blob buffer too small (%llu < %llu)", (unsigned long long)bytes, (unsigned long long)need);
+    BihHeader h;
+    if ((rc = fetch_header(c, &h))) return rc;
+    const size_t nb = (size_t)(h.nu > 1 ? h.nu - 1 : 0) * 16, tb = (size_t)h.n * 48;
+    uint8_t* d = (uint8_t*)dev_dst;
+    BIHRT_CUDA(c, cudaMemcpyAsync(d, c->d_hdr, 64, cudaMemcpyDeviceToDevice, c->stream));
+    if (nb) BIHRT_CUDA(c, cudaMemcpyAsync(d + 64, c->d_nodes, nb, cudaMemcpyDeviceToDevice, c->stream));
+    if (tb) BIHRT_CUDA(c, cudaMemcpyAsync(d + 64 + nb, c->d_tris, tb, cudaMemcpyDeviceToDevice, c->stream));
+    return BIHRT_OK;
+}
+
+int bihrt_bih_import(bihrt_ctx* c, const void* dev_src, uint64_t bytes) {
+    ENTER(c);
+    if (!dev_src || bytes < 64) return bihrt_fail(c, BIHRT_ERR_INVALID, "bad blob");
+    BihHeader h;
+    BIHRT_CUDA(c, cudaMemcpyAsync(&h, dev_src, 64, cudaMemcpyDeviceToHost, c->stream));
+    BIHRT_CUDA(c, cudaStreamSynchronize(c->stream));
+    const size_t nb = (size_t)(h.nu > 1 ? h.nu - 1 : 0) * 16, tb = (size_t)h.n * 48;
+    if (h.nu > h.n || bytes < 64 + nb + tb) return bihrt_fail(c, BIHRT_ERR_INVALID, "blob truncated or corrupt");
+    int rc = ensure_capacity(c, h.n, false);
+    if (rc) return rc;
+    const uint8_t* s = (const uint8_t*)dev_src;
+    BIHRT_CUDA(c, cudaMemcpyAsync(c->d_hdr, s, 64, cudaMemcpyDeviceToDevice, c->stream));
+    if (nb) BIHRT_CUDA(c, cudaMemcpyAsync(c->d_nodes, s + 64, nb, cudaMemcpyDeviceToDevice, c->stream));
+    if (tb) BIHRT_CUDA(c, cudaMemcpyAsync(c->d_tris, s + 64 + nb, tb, cudaMemcpyDeviceToDevice, c->stream));
+    c->n = h.n; c->built = true; c->build_timed = false;
+    return BIHRT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,151 @@
+// Internal declarations shared by build.cu, trace.cu and api.cu.  sm_100a only.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include "../../include/bihrt.h"
+
+// -------------------------------------------------------------------------------------------
+// HBM layout of a built BIH (DESIGN.md "Data layout")
+// -------------------------------------------------------------------------------------------
+// Node, 16 B, one LDG.128 per visit.  Index = the reference's (Karras) node index, so node i here is
+// TreeInternalNode i of R/src/Tree.cuh:16-24.  A child reference packs
+//   bit 31    : child is a leaf
+//   bit 30    : one bit of the split axis (ref_l: axis&1, ref_r: axis>>1)
+//   bits 29..0: internal child -> node index; leaf child -> first slot of the leaf in tris[]
+struct __align__(16) BihNode {
+    float    clip0;   // max over the left subtree of hi[axis]   (t_clipPlanes[0])
+    float    clip1;   // min over the right subtree of lo[axis]  (t_clipPlanes[1])
+    uint32_t ref_l;
+    uint32_t ref_r;
+};
+#define BIH_REF_LEAF  0x80000000u
+#define BIH_REF_AXIS  0x40000000u
+#define BIH_REF_INDEX 0x3FFFFFFFu
+
+// Leaf-ordered triangle, 48 B = 3 x LDG.128: v0, e1 = v1 - v0, e2 = v2 - v0 (the two edges
+// RayTriangleIntersection recomputes per test, R/src/CUDAKernels.cu:18-19), the input triangle index
+// (m_trisIndexes[slot]) and an end-of-leaf flag.  Slot order = Morton-sorted order, so a leaf is a
+// contiguous run and the reference's triangleIdxs[] / firstIdxs[] / duplicatesCnts[] indirections
+// (R/src/CUDAKernels.cu:215-217) are gone from the traversal.
+struct __align__(16) BihTri {
+    float    v0x, v0y, v0z, e1x;
+    float    e1y, e1z, e2x, e2y;
+    float    e2z;
+    uint32_t prim;
+    uint32_t last;     // 1 on the last triangle of its leaf
+    uint32_t pad;
+};
+
+struct SceneBox { float lo[3]; float hi[3]; };
+
+// Device-resident header of a built BIH; lives at the start of the blob that is broadcast.
+struct BihHeader {
+    uint32_t n;          // triangles
+    uint32_t nu;         // leaves
+    float    lo[3];      // scene box
+    float    hi[3];
+    uint32_t status;     // 0 ok, !=0 device watchdog
+    uint32_t pad[7];
+};
+static_assert(sizeof(BihHeader) == 64, "header is one 64-byte line");
+
+// -------------------------------------------------------------------------------------------
+// context
+// -------------------------------------------------------------------------------------------
+struct bihrt_ctx {
+    int          device = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;
+    std::string  err;
+    int          sm_count = 148;
+
+    // scene (input order)
+    float*   d_tri_in = nullptr;     // n x 9 floats (reference Triangle layout, 36 B)
+    int64_t  n = 0, cap_n = 0;
+    bool     have_scene = false, built = false;
+
+    // BIH blob: [BihHeader | nodes (nu-1, padded) | tris (n)]  -- one allocation, one broadcast
+    uint8_t* d_blob = nullptr;
+    size_t   blob_cap = 0;
+    BihHeader* d_hdr = nullptr;
+    BihNode*   d_nodes = nullptr;
+    BihTri*    d_tris = nullptr;
+
+    // build scratch (all sized by cap_n)
+    uint32_t *d_keys[2] = {nullptr, nullptr}, *d_vals[2] = {nullptr, nullptr};
+    uint32_t *d_umc = nullptr;        // unique codes [nu]
+    uint32_t *d_first = nullptr;      // first slot of each leaf [nu+1]
+    uint32_t *d_hist = nullptr;       // 4 x 256 digit histograms + tile counters + misc
+    uint32_t *d_lookback = nullptr;   // onesweep / RLE decoupled look-back words
+    size_t    lookback_words = 0;
+    int32_t  *d_arrive = nullptr;     // agglomerative build: other child's range end, -1 = nobody yet
+    float    *d_boxscratch = nullptr; // 6 floats per split
+    uint32_t *d_scenebox_enc = nullptr; // 6 order-preserving encoded floats
+
+    // trace
+    uint32_t* d_fb = nullptr; int fb_w = 0, fb_h = 0; size_t fb_cap = 0;
+    void*     d_io = nullptr; size_t io_cap = 0;      // staging for host ray lists / results
+    unsigned long long* d_counters = nullptr;
+    uint32_t* d_work = nullptr;                        // persistent-kernel work counter
+
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool        build_timed = false;
+
+    // options
+    int opt_trace_block = 128;
+    int opt_trace_blocks_per_sm = 0;   // 0 = occupancy query
+    int opt_trace_variant = 0;
+    int opt_sort_passes = 4;
+};
+
+int  bihrt_fail(bihrt_ctx* c, int code, const char* fmt, ...);
+#define BIHRT_CUDA(c, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+    return bihrt_fail((c), BIHRT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+// build.cu
+int bihrt_build_launch(bihrt_ctx* c);
+// trace.cu
+struct TraceArgs {
+    const BihHeader* hdr; const BihNode* nodes; const BihTri* tris;
+    const bihrt_ray* rays; int64_t nrays;
+    float* out_t; int32_t* out_slot; int32_t* out_prim;
+    // camera mode
+    bihrt_camera cam; int w, h, spp; uint64_t seed; uint32_t flags; int shard_index, shard_count;
+    uint32_t* fb;
+    unsigned long long* counters; uint32_t* work;
+};
+int bihrt_trace_launch(bihrt_ctx* c, const TraceArgs& a, int mode /*0 rays,1 render fb,2 render hits*/, bool counted);
+
+// -------------------------------------------------------------------------------------------
+// device helpers
+// -------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+// order-preserving float <-> uint (sign-magnitude total order, -0 < +0): lets scene-box min/max be
+// plain integer atomics (the reference's atomicMin/MaxFloat trick, R/src/CUDAKernels.cu:52-66)
+__device__ __forceinline__ uint32_t enc_float(float f) {
+    uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float dec_float(uint32_t u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
+}
+
+// counter-based jitter, bit-identical to oracle/bih_oracle.c:jitter01 (replaces curand XORWOW,
+// R/src/CUDAKernels.cu:411-419,458)
+__host__ __device__ __forceinline__ uint32_t bihrt_mix32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+__device__ __forceinline__ float bihrt_jitter(uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t dim) {
+    uint32_t h = bihrt_mix32((uint32_t)seed ^ bihrt_mix32(pixel + 0x9e3779b9u * (sample * 2u + dim + 1u)) ^ (uint32_t)(seed >> 32));
+    return __fmul_rn((float)((h >> 8) + 1u), 1.0f / 16777216.0f);
+}
+
+__device__ __forceinline__ uint32_t ld_relaxed(const uint32_t* p) {
+    uint32_t v; asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ void st_relaxed(uint32_t* p, uint32_t v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+#endif

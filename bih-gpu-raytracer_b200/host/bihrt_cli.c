@@ -1,0 +1,97 @@
+/*
+ * bihrt_cli.c -- C host program on top of the C ABI (include/bihrt.h).
+ *
+ * The headless counterpart of the reference's entry point and frame loop
+ * (main(), R/src/Main.cpp:44-68; App::LoadModels, R/src/App.cpp:65-167; App::Run, R/src/App.cpp:170-187;
+ * Renderer::Render, R/src/Renderer.cpp:415-672): load a mesh, then per frame rebuild the BIH and render
+ * with the reference's camera, resolution and samples per pixel; the packed framebuffer is written as a
+ * PPM instead of being presented through OpenGL (R/src/Renderer.cpp:644-670).
+ *
+ *   bihrt_cli <mesh.obj | mesh.tri9> [-w 640] [-h 480] [-s 4] [-f frames] [-o out.ppm] [-d device]
+ *   (.tri9 = raw little-endian float32, 9 floats per triangle)
+ */
+#define _POSIX_C_SOURCE 200809L
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+#include "bihrt.h"
+
+static double now_ms(void) {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
+#define CHECK(call) do { int rc_ = (call); if (rc_ != BIHRT_OK) { \
+    fprintf(stderr, "%s -> %d: %s\n", #call, rc_, ctx ? bihrt_last_error(ctx) : "(no context)"); \
+    if (ctx) { bihrt_destroy(ctx); } return 1; } } while (0)
+
+int main(int argc, char** argv) {
+    const char* path = NULL; const char* out = "frame.ppm";
+    int w = 640, h = 480, spp = 4, frames = 1, device = 0;     /* R/src/Constants.h:4-8 */
+    for (int i = 1; i < argc; i++) {
+        if (!strcmp(argv[i], "-w") && i + 1 < argc) w = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "-h") && i + 1 < argc) h = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "-s") && i + 1 < argc) spp = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "-f") && i + 1 < argc) frames = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "-o") && i + 1 < argc) out = argv[++i];
+        else if (!strcmp(argv[i], "-d") && i + 1 < argc) device = atoi(argv[++i]);
+        else path = argv[i];
+    }
+    if (!path) { fprintf(stderr, "usage: %s <mesh.obj|mesh.tri9> [-w W] [-h H] [-s spp] [-f frames] [-o out.ppm] [-d dev]\n", argv[0]); return 2; }
+
+    bihrt_ctx* ctx = NULL;
+    bihrt_config cfg; memset(&cfg, 0, sizeof cfg); cfg.device = device;
+    CHECK(bihrt_create(&ctx, &cfg));
+
+    size_t len = strlen(path);
+    if (len > 5 && !strcmp(path + len - 5, ".tri9")) {
+        FILE* f = fopen(path, "rb");
+        if (!f) { fprintf(stderr, "cannot open %s\n", path); bihrt_destroy(ctx); return 1; }
+        fseek(f, 0, SEEK_END); long bytes = ftell(f); fseek(f, 0, SEEK_SET);
+        float* tri = (float*)malloc((size_t)bytes);
+        if (!tri || fread(tri, 1, (size_t)bytes, f) != (size_t)bytes) { fprintf(stderr, "read failed\n"); fclose(f); bihrt_destroy(ctx); return 1; }
+        fclose(f);
+        CHECK(bihrt_scene_load_triangles(ctx, tri, (int64_t)(bytes / 36)));
+        CHECK(bihrt_sync(ctx));
+        free(tri);
+    } else {
+        CHECK(bihrt_scene_load_obj(ctx, path));
+    }
+
+    /* Camera((2,0,-2), W/H), R/src/Renderer.cpp:99, R/src/Camera.cu:5-9 */
+    const float aspect = (float)w / (float)h;
+    bihrt_camera cam = { { 2.0f, 0.0f, -2.0f }, { 0.0f, -1.0f, -1.0f }, { aspect * 2.0f, 0.0f, 0.0f }, { 0.0f, 2.0f, 0.0f } };
+
+    bihrt_build_info info;
+    for (int f = 0; f < frames; f++) {                         /* the reference rebuilds every frame */
+        double t0 = now_ms();
+        CHECK(bihrt_build(ctx));
+        CHECK(bihrt_render(ctx, &cam, w, h, spp, 1984u + (uint64_t)f, BIHRT_RENDER_JITTER));
+        CHECK(bihrt_sync(ctx));
+        double t1 = now_ms();
+        CHECK(bihrt_get_build_info(ctx, &info));
+        printf("frame %d: %lld triangles, %lld leaves, build %.3f ms (device), frame %.3f ms (host), %.1f Mrays/s incl. build\n",
+               f, (long long)info.n, (long long)info.nu, info.last_build_ms, t1 - t0, (double)w * h * spp / ((t1 - t0) * 1e3));
+    }
+
+    uint32_t* fb = (uint32_t*)malloc((size_t)w * h * 4);
+    CHECK(bihrt_framebuffer_read(ctx, fb));
+    FILE* o = fopen(out, "wb");
+    if (o) {
+        fprintf(o, "P6\n%d %d\n255\n", w, h);
+        for (int j = h - 1; j >= 0; j--)                       /* row 0 = bottom */
+            for (int i = 0; i < w; i++) {
+                uint32_t p = fb[(size_t)j * w + i];
+                unsigned char rgb[3] = { (unsigned char)(p & 255), (unsigned char)((p >> 8) & 255), (unsigned char)((p >> 16) & 255) };
+                fwrite(rgb, 1, 3, o);
+            }
+        fclose(o);
+        printf("wrote %s\n", out);
+    }
+    free(fb);
+    bihrt_destroy(ctx);
+    return 0;
+}

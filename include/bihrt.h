@@ -1,0 +1,164 @@
+/*
+ * bihrt.h -- C ABI of libbihrt.so: B200-native (sm_100a) BIH build + ray traversal + ray/triangle
+ * intersection, a drop-in for the hot path of rehakvoj1/BIH-GPU-Raytracer.
+ *
+ * The reference has no FFI/plugin interface: the path sits behind three C++ classes with
+ * thrust-typed members (App, Renderer, GPUArrayManager).  The boundary kept here is the set of
+ * entry points and their data contracts; each export cites what it replaces.
+ * R/ = BIH_Raytracer/BIH_Raytracer/ of the reference tree.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every function returns BIHRT_OK (0) or a negative code and
+ *     never exits the process (the reference prints and calls exit(99), R/src/Renderer.cpp:63-73);
+ *     bihrt_last_error() gives the message of the last failure on that context.
+ *   - pointer arguments marked "host or device" are classified with cudaPointerGetAttributes.
+ *   - one context = one GPU, one stream; calls are asynchronous on that stream unless they return
+ *     data to host memory.  One context per host thread.
+ *   - there is NO CPU fallback: every compute entry point fails if no sm_100-class GPU is present.
+ */
+#ifndef BIHRT_H
+#define BIHRT_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define BIHRT_API __attribute__((visibility("default")))
+#else
+#define BIHRT_API
+#endif
+
+#define BIHRT_VERSION 100
+
+#define BIHRT_OK             0
+#define BIHRT_ERR_INVALID   -1   /* bad argument */
+#define BIHRT_ERR_CUDA      -2   /* CUDA runtime error (message has the CUDA string) */
+#define BIHRT_ERR_NOMEM     -3   /* device or host allocation failed (reference: Allocate* -> false) */
+#define BIHRT_ERR_STATE     -4   /* call order: no scene loaded / BIH not built */
+#define BIHRT_ERR_IO        -5   /* OBJ file unreadable or malformed */
+#define BIHRT_ERR_INTERNAL  -6   /* device-side watchdog tripped (never expected) */
+
+typedef struct bihrt_ctx bihrt_ctx;
+
+/* Run-time replacement of the compile-time macros in R/src/Constants.h:4-8. */
+typedef struct bihrt_config {
+    int32_t  device;        /* CUDA device ordinal */
+    uint32_t flags;         /* reserved, 0 */
+    int32_t  reserved[6];
+} bihrt_config;
+
+/* Camera, same four vectors as R/src/Camera.h:14-17; ray(u,v) = (origin,
+ * lower_left + u*horizontal + v*vertical - origin), NOT normalised (R/src/Camera.cu:18-20). */
+typedef struct bihrt_camera {
+    float origin[3];
+    float lower_left[3];
+    float horizontal[3];
+    float vertical[3];
+} bihrt_camera;
+
+/* Ray = origin + direction (R/src/Ray.h:19-20); invDir/sign are derived inside (R/src/Ray.cu:3-10). */
+typedef struct bihrt_ray {
+    float o[3];
+    float d[3];
+} bihrt_ray;
+
+/* bihrt_render flags */
+#define BIHRT_RENDER_JITTER   1u   /* jittered samples (reference behaviour); otherwise pixel centres */
+
+/* Reference view of a built BIH: arrays with the exact field meaning of the reference's device
+ * arrays.  Caller allocates; any pointer may be NULL to skip that array.
+ * Capacities: [n] for the per-triangle arrays, [nu] / [nu-1] for the per-cell / per-node ones
+ * (allocating n entries for each is always enough). */
+typedef struct bihrt_refview {
+    int64_t   n;                    /* out: triangles */
+    int64_t   nu;                   /* out: unique Morton cells = leaves (GetUniqueMCSize) */
+    float     scene_lo[3];          /* out: AABBs::sceneBBoxLo, R/src/AABB.h:15 */
+    float     scene_hi[3];          /* out: AABBs::sceneBBoxHi */
+    uint32_t* morton_codes;         /* [n]    m_mortonCodes after the sort */
+    uint32_t* tris_indexes;         /* [n]    m_trisIndexes: sorted slot -> input triangle */
+    uint32_t* unique_morton_codes;  /* [nu]   m_uniqueMortonCodes */
+    uint32_t* duplicates_cnts;      /* [nu]   m_duplicatesCnts */
+    int32_t*  first_idxs;           /* [nu]   m_firstIdxs */
+    float*    clip_planes;          /* [2*(nu-1)] TreeInternalNode::t_clipPlanes, R/src/Tree.cuh:17 */
+    int32_t*  axis;                 /* [nu-1] t_axis */
+    uint8_t*  is_leaf;              /* [2*(nu-1)] isLeaf */
+    int32_t*  children;             /* [2*(nu-1)] children */
+    int32_t*  parent;               /* [nu-1] parent (root: -1) */
+    int32_t*  leaf_parents;         /* [nu]   m_leafParents */
+} bihrt_refview;
+
+typedef struct bihrt_build_info {
+    int64_t n;                /* triangles */
+    int64_t nu;               /* leaves */
+    int64_t node_bytes;       /* compact nodes, 16 B each */
+    int64_t tri_bytes;        /* leaf-ordered triangles, 48 B each */
+    float   last_build_ms;    /* device time of the last bihrt_build (CUDA events) */
+    int32_t sort_passes;
+    int32_t reserved[6];
+} bihrt_build_info;
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+BIHRT_API int         bihrt_version(void);
+BIHRT_API int         bihrt_create(bihrt_ctx** out, const bihrt_config* cfg);   /* replaces Renderer::Init + GPUArrayManager ctor, R/src/Renderer.cpp:87-105 */
+BIHRT_API void        bihrt_destroy(bihrt_ctx* ctx);
+BIHRT_API const char* bihrt_last_error(const bihrt_ctx* ctx);                   /* replaces checkCudaErrors' stderr print */
+BIHRT_API int         bihrt_set_stream(bihrt_ctx* ctx, void* cuda_stream);      /* run on a caller-owned stream (NULL = own stream) */
+BIHRT_API int         bihrt_sync(bihrt_ctx* ctx);                               /* replaces the cudaDeviceSynchronize after each step, R/src/Renderer.cpp:428-503 */
+BIHRT_API int         bihrt_set_option(bihrt_ctx* ctx, const char* name, int64_t value);  /* tuning knobs, see DESIGN.md */
+
+/* ---- scene load: App::LoadModels + GPUArrayManager::Allocate*, R/src/App.cpp:65-167,
+ *      R/src/GPUArrayManager.cpp:7-91.  xyz9 = n x (v0,v1,v2) floats in model->mesh->face order,
+ *      host or device; the library copies. ------------------------------------------------------ */
+BIHRT_API int bihrt_scene_load_triangles(bihrt_ctx* ctx, const float* xyz9, int64_t n);
+BIHRT_API int bihrt_scene_update_vertices(bihrt_ctx* ctx, const float* xyz9, int64_t n);  /* animation: same n, BIH becomes stale */
+BIHRT_API int bihrt_scene_load_obj(bihrt_ctx* ctx, const char* path);          /* minimal Wavefront reader replacing Model(path), R/src/Model.cpp:10-29 */
+
+/* ---- build: first half of Renderer::Render (Morton transform, sort, RLE, Launch_BuildTree,
+ *      Launch_FindClipPlanes), R/src/Renderer.cpp:422-503.  No host sync inside. ------------------ */
+BIHRT_API int bihrt_build(bihrt_ctx* ctx);
+BIHRT_API int bihrt_get_build_info(bihrt_ctx* ctx, bihrt_build_info* out);     /* synchronises */
+BIHRT_API int bihrt_export_reference_view(bihrt_ctx* ctx, bihrt_refview* view); /* synchronises; see bihrt_refview */
+
+/* ---- trace: Launch_cudaRender -> cudaRender -> TraverseTree, R/src/CUDAKernels.cu:227-447.
+ *      Per ray: t in units of |d| (FLT_MAX on miss), slot = index into the Morton-sorted triangle
+ *      order (the reference's HitRecord::triangleIdx, R/src/CUDAKernels.cu:215-221; -1 on miss),
+ *      prim = input triangle index = tris_indexes[slot].  rays / outputs: host or device; any
+ *      output may be NULL. ---------------------------------------------------------------------- */
+BIHRT_API int bihrt_trace(bihrt_ctx* ctx, const bihrt_ray* rays, int64_t n, float* t, int32_t* slot, int32_t* prim);
+/* instrumented trace: counters[0]=internal nodes visited, [1]=triangle tests, [2]=max stack depth,
+ * [3]=rays; same results as bihrt_trace (outputs may be NULL). */
+BIHRT_API int bihrt_trace_counted(bihrt_ctx* ctx, const bihrt_ray* rays, int64_t n, float* t, int32_t* slot,
+                        int32_t* prim, uint64_t counters[4]);
+
+/* Render w x h pixels, spp samples each, into the context's framebuffer with the reference's
+ * colouring: hit (255,255,0), miss (20,20,40), mean over samples, packed r | g<<8 | b<<16, row 0 =
+ * bottom (R/src/CUDAKernels.cu:82-88,385-387,391-423).  Jitter comes from a counter-based hash of
+ * (seed, pixel, sample) instead of per-pixel XORWOW state (documented difference). */
+BIHRT_API int bihrt_render(bihrt_ctx* ctx, const bihrt_camera* cam, int32_t w, int32_t h, int32_t spp,
+                 uint64_t seed, uint32_t flags);
+/* Multi-GPU: render only the 32x32-pixel tiles with tile_id % shard_count == shard_index; every
+ * other pixel of the framebuffer is set to 0, so a sum (or bitwise OR) of the shards' framebuffers
+ * is the full image. */
+BIHRT_API int bihrt_render_shard(bihrt_ctx* ctx, const bihrt_camera* cam, int32_t w, int32_t h, int32_t spp,
+                       uint64_t seed, uint32_t flags, int32_t shard_index, int32_t shard_count);
+/* Per-sample hit buffers of the same rays bihrt_render traces (index = (j*w+i)*spp + s); device or
+ * host outputs, any may be NULL.  Used by the parity tests. */
+BIHRT_API int bihrt_render_hits(bihrt_ctx* ctx, const bihrt_camera* cam, int32_t w, int32_t h, int32_t spp,
+                      uint64_t seed, uint32_t flags, float* t, int32_t* slot, int32_t* prim);
+
+/* ---- framebuffer: Renderer::m_cudaDestResource, R/src/Renderer.h:46, R/src/Renderer.cpp:762-768 */
+BIHRT_API int bihrt_framebuffer(bihrt_ctx* ctx, uint32_t** dev_ptr, int32_t* w, int32_t* h);  /* device pointer, owned by ctx */
+BIHRT_API int bihrt_framebuffer_read(bihrt_ctx* ctx, uint32_t* host_dst);                      /* synchronises */
+
+/* ---- BIH replication across GPUs (one broadcast of this blob per build) ------- */
+BIHRT_API int bihrt_bih_blob_bytes(bihrt_ctx* ctx, uint64_t* bytes);                     /* synchronises (needs Nu) */
+BIHRT_API int bihrt_bih_export(bihrt_ctx* ctx, void* dev_dst, uint64_t bytes);           /* device buffer, D2D on the ctx stream */
+BIHRT_API int bihrt_bih_import(bihrt_ctx* ctx, const void* dev_src, uint64_t bytes);     /* adopt a blob built on another GPU */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BIHRT_H */

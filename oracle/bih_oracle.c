@@ -435,11 +435,13 @@ static void traverse_ref(const orc_scene* s, const orc_ray* r, orc_hit* rec, orc
  * It carries two intervals: the reference's own tMin (rMin: overwritten on far descents exactly as
  * R/src/CUDAKernels.cu:331,354,359) and a tight interval [pMin,pMax] (interval INTERSECTION, pMin
  * clamped to 0 because hits need t > 0 (:218), pMax also bounded by the closest hit so far).
- *   near child visited  <=>  reference's strict test (rMin < t[near], :292)  AND  the CLOSED tight
- *                            interval [pMin, min(pMax, t[near], best)] is non-empty;
- *   far child visited   <=>  the CLOSED tight interval [max(pMin, t[far]), min(pMax, best)] is
- *                            non-empty (this implies the reference's !(tMax < t[far]), :293,
- *                            because the reference's tMax is never below pMax).
+ *   near child considered <=> reference's strict test (rMin < t[near], :292)  AND  the CLOSED tight
+ *                             interval [pMin, min(pMax, t[near])] is non-empty;
+ *   far child considered  <=> the CLOSED tight interval [max(pMin, t[far]), pMax] is non-empty
+ *                             (this implies the reference's !(tMax < t[far]), :293, because the
+ *                             reference's tMax is never below pMax);
+ *   a considered child (leaf or node) is actually entered only if its tight interval, cut at the
+ *   closest hit found so far, is still non-empty at the moment it is entered.
  * So the visited leaves are a subset of the reference's, and a leaf is only dropped when its
  * tight interval is empty or starts beyond the closest hit: the result equals TraverseTree's
  * except when Moller-Trumbore's rounded t disagrees with the rounded plane distances at an
@@ -458,47 +460,36 @@ static void traverse_proper(const orc_scene* s, const orc_ray* r, orc_hit* rec, 
     int sp = 0;
     int cur = 0;
     for (;;) {
-        c->nodes++;
-        int ax = s->axis[cur];
-        float org = r->o[ax], inv = r->inv[ax];
-        int near = r->sign[ax], far = 1 - near;
-        float t0 = (s->clip[2 * cur] - org) * inv;
-        float t1 = (s->clip[2 * cur + 1] - org) * inv;
-        float tn = near ? t1 : t0, tf = near ? t0 : t1;
-        float nMax = dev_fminf(dev_fminf(pMax, tn), (float)rec->t);   /* near: [pMin, nMax] */
-        float fMin = dev_fmaxf(pMin, tf);                             /* far : [fMin, fMax] */
-        int go_near = (rMin < tn) && (pMin <= nMax);
-        const uint8_t* lf = s->is_leaf + 2 * cur;
-        const int32_t* ch = s->children + 2 * cur;
-        int next = -1;
-        float n_rMin = rMin, n_pMin = pMin, n_pMax = pMax;
-        if (go_near) {
-            if (lf[near]) find_nearest(s, r, ch[near], rec, c);
-            else { next = ch[near]; n_pMax = dev_fminf(pMax, tn); }
-        }
-        float fMax = dev_fminf(pMax, (float)rec->t);                  /* after a near LEAF test */
-        int go_far = (fMin <= fMax);
-        if (go_far) {
-            if (lf[far]) {
-                /* reference order: a far leaf is tested at this node, before the near subtree */
-                find_nearest(s, r, ch[far], rec, c);
-            } else if (next >= 0) {
+        /* entry check: tight interval, shrunk to the closest hit so far, must be non-empty (closed) */
+        if (pMin <= dev_fminf(pMax, (float)rec->t)) {
+            c->nodes++;
+            int ax = s->axis[cur];
+            float org = r->o[ax], inv = r->inv[ax];
+            int near = r->sign[ax], far = 1 - near;
+            float t0 = (s->clip[2 * cur] - org) * inv;
+            float t1 = (s->clip[2 * cur + 1] - org) * inv;
+            float tn = near ? t1 : t0, tf = near ? t0 : t1;
+            const uint8_t* lf = s->is_leaf + 2 * cur;
+            const int32_t* ch = s->children + 2 * cur;
+            int near_ok = (rMin < tn);                              /* the reference's strict test, :292 */
+            float nMax = dev_fminf(pMax, tn);                       /* near: [pMin, nMax] */
+            float fMin = dev_fmaxf(pMin, tf);                       /* far : [fMin, pMax] */
+            /* leaf children are tested here, near first (reference order :337-338,346,352) */
+            if (near_ok && lf[near] && pMin <= dev_fminf(nMax, (float)rec->t)) find_nearest(s, r, ch[near], rec, c);
+            if (lf[far] && fMin <= dev_fminf(pMax, (float)rec->t)) find_nearest(s, r, ch[far], rec, c);
+            int near_i = near_ok && !lf[near] && (pMin <= nMax);
+            int far_i = !lf[far] && (fMin <= pMax);
+            if (near_i && far_i) {
                 stack[sp].node = ch[far]; stack[sp].rMin = tf; stack[sp].pMin = fMin; stack[sp].pMax = pMax; sp++;
                 if (sp > c->max_stack) c->max_stack = sp;
-            } else { next = ch[far]; n_rMin = tf; n_pMin = fMin; }
+                cur = ch[near]; pMax = nMax;
+                continue;
+            } else if (near_i) { cur = ch[near]; pMax = nMax; continue; }
+            else if (far_i) { cur = ch[far]; rMin = tf; pMin = fMin; continue; }
         }
-        if (next >= 0) { cur = next; rMin = n_rMin; pMin = n_pMin; pMax = n_pMax; continue; }
-        /* pop; skip entries whose tight interval is empty after shrinking to the closest hit */
-        int found = 0;
-        while (sp > 0) {
-            sp--;
-            float q = dev_fminf(stack[sp].pMax, (float)rec->t);
-            if (stack[sp].pMin <= q) {
-                cur = stack[sp].node; rMin = stack[sp].rMin; pMin = stack[sp].pMin; pMax = stack[sp].pMax;
-                found = 1; break;
-            }
-        }
-        if (!found) break;
+        if (sp == 0) break;
+        sp--;
+        cur = stack[sp].node; rMin = stack[sp].rMin; pMin = stack[sp].pMin; pMax = stack[sp].pMax;
     }
 }
 

@@ -1,0 +1,118 @@
+"""GPU BIH build vs the oracle: every array of the reference's data model, bit for bit, through the C ABI."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import assert_view_equals_oracle
+from test_oracle_kat import GOLD, check_against_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def build_view(renderer, tri):
+    renderer.load_models(tri).build()
+    return renderer.reference_view()
+
+
+def test_kat_dodecahedron_matches_reference_dump(renderer, scenes, oracle):
+    v = build_view(renderer, scenes.dodecahedron(True))
+    gold = json.load(open(GOLD))
+    check_against_golden(v["children"], v["is_leaf"], v["axis"], v["parent"], v["clip_planes"], gold["nodes"])
+    assert_view_equals_oracle(v, oracle.Bih(scenes.dodecahedron(True)))
+
+
+@pytest.mark.parametrize("name", ["cornell", "sphere16", "sphere187", "atrium", "soup", "duplicates", "flat", "sphere361"])
+def test_build_bit_exact(renderer, scenes, oracle, name):
+    tri = {
+        "cornell": lambda: scenes.cornell_box(),
+        "sphere16": lambda: scenes.displaced_sphere(16),
+        "sphere187": lambda: scenes.displaced_sphere(187),
+        "sphere361": lambda: scenes.displaced_sphere(361),
+        "atrium": lambda: scenes.atrium(),
+        "soup": lambda: scenes.random_soup(100000),
+        "duplicates": lambda: np.repeat(scenes.dodecahedron(), 5, axis=0),
+        "flat": lambda: scenes.quad_grid([0, 0, 0], [1, 0, 0], [0, 1, 0], 40, 30),
+    }[name]()
+    assert_view_equals_oracle(build_view(renderer, tri), oracle.Bih(tri))
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 31, 32, 33, 255, 256, 257, 4095, 4096, 4097, 8193])
+def test_ragged_sizes(renderer, scenes, oracle, n):
+    tri = scenes.random_soup(n, size=0.1, seed=n)
+    assert_view_equals_oracle(build_view(renderer, tri), oracle.Bih(tri))
+
+
+def test_single_cell_and_empty(renderer, oracle):
+    same = np.tile(np.array([[0, 0, 0, 1, 0, 0, 0, 1, 0]], np.float32), (7, 1))
+    v = build_view(renderer, same)
+    assert v["nu"] == 1 and v["n"] == 7 and len(v["axis"]) == 0
+    assert_view_equals_oracle(v, oracle.Bih(same))
+    renderer.load_models(np.zeros((0, 9), np.float32)).build()
+    assert renderer.build_info()["nu"] == 0
+
+
+def test_rebuild_is_idempotent_and_update_vertices(renderer, scenes, oracle):
+    a, b = scenes.displaced_sphere(64, phase=0.0), scenes.displaced_sphere(64, phase=0.7)
+    renderer.load_models(a).build()
+    v1 = renderer.reference_view()
+    renderer.build()
+    v2 = renderer.reference_view()
+    for k in ("morton_codes", "tris_indexes", "children", "clip_planes", "parent"):
+        np.testing.assert_array_equal(v1[k], v2[k])
+    renderer.update_vertices(b)
+    renderer.build()                       # animation: clip planes must be rebuilt from scratch
+    assert_view_equals_oracle(renderer.reference_view(), oracle.Bih(b))
+
+
+def test_device_pointer_input(renderer, scenes, oracle):
+    import torch
+    tri = scenes.displaced_sphere(48)
+    d = torch.from_numpy(tri).cuda()
+    renderer.load_models(d).build()
+    assert_view_equals_oracle(renderer.reference_view(), oracle.Bih(tri))
+
+
+def test_one_million_triangles(renderer, scenes, oracle):
+    """BASELINE config 5 size: full comparison with the oracle (the CPU build takes < 1 s) plus the
+    size-independent properties: sortedness, permutation, run structure, tree shape."""
+    tri = scenes.displaced_sphere(708)
+    v = build_view(renderer, tri)
+    n, nu = v["n"], v["nu"]
+    assert n == 1002528
+    codes = v["morton_codes"]
+    assert np.all(codes[1:] >= codes[:-1])
+    assert np.array_equal(np.sort(v["tris_indexes"]), np.arange(n, dtype=np.uint32))
+    eq = codes[1:] == codes[:-1]                      # stable: equal codes keep input order
+    assert np.all(v["tris_indexes"][1:][eq] > v["tris_indexes"][:-1][eq])
+    assert v["duplicates_cnts"].sum() == n and np.all(np.diff(v["unique_morton_codes"].astype(np.int64)) > 0)
+    ch, lf = v["children"], v["is_leaf"]
+    assert np.all(ch[:, 1] == ch[:, 0] + 1)
+    assert lf.sum() == nu and (~lf.astype(bool)).sum() == nu - 2     # every leaf / non-root node has one parent
+    assert_view_equals_oracle(v, oracle.Bih(tri))
+
+
+def test_obj_loader(renderer, scenes, oracle, tmp_path):
+    tri = scenes.dodecahedron()
+    p = tmp_path / "d.obj"
+    with open(p, "w") as f:
+        f.write("# test\n")
+        for t in tri.reshape(-1, 3):
+            f.write("v %.9g %.9g %.9g\n" % tuple(t))
+        for i in range(len(tri)):
+            f.write("f %d/1/1 %d//2 %d\n" % (3 * i + 1, 3 * i + 2, 3 * i + 3))
+        f.write("v 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nf -4 -3 -2 -1\n")     # quad -> fan of 2
+    renderer.load_models(str(p)).build()
+    quad = np.array([[0, 0, 0, 1, 0, 0, 1, 1, 0], [0, 0, 0, 1, 1, 0, 0, 1, 0]], np.float32)
+    assert_view_equals_oracle(renderer.reference_view(), oracle.Bih(np.concatenate([tri, quad])))
+
+
+def test_error_codes(renderer):
+    import bihrt
+    with pytest.raises(bihrt.BihrtError) as e:
+        renderer.build()
+    assert e.value.code == -4
+    with pytest.raises(bihrt.BihrtError) as e:
+        renderer.load_models("/nonexistent/file.obj")
+    assert e.value.code == -5

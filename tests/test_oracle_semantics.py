@@ -1,0 +1,117 @@
+"""Oracle self-consistency: reference-semantics traversal == pruned traversal (always) == brute force
+(on scenes without axis-aligned flat geometry, where the reference itself drops boundary hits)."""
+import numpy as np
+import pytest
+
+
+def _rays(oracle, scenes, cam, w, h, **kw):
+    return oracle.camera_rays(cam, w, h, **kw)
+
+
+@pytest.mark.parametrize("name", ["dodecahedron", "cornell", "sphere16", "sphere187", "atrium", "soup"])
+def test_pruned_traversal_equals_reference_traversal(oracle, scenes, name):
+    tri, cam, w, h = {
+        "dodecahedron": (scenes.dodecahedron(), scenes.pinhole_camera(aspect=1.0), 96, 96),
+        "cornell": (scenes.cornell_box(), scenes.cornell_camera(), 256, 256),
+        "sphere16": (scenes.displaced_sphere(16), scenes.pinhole_camera(), 160, 90),
+        "sphere187": (scenes.displaced_sphere(187), scenes.pinhole_camera(), 320, 180),
+        "atrium": (scenes.atrium(0.05), scenes.atrium_camera(), 240, 135),
+        "soup": (scenes.random_soup(20000), scenes.pinhole_camera(), 160, 90),
+    }[name]
+    b = oracle.Bih(tri)
+    rays = _rays(oracle, scenes, cam, w, h, spp=2, jitter=True)
+    t0, s0, p0, c0 = b.trace(rays, "ref", want_counters=True)
+    t1, s1, p1, c1 = b.trace(rays, "proper", want_counters=True)
+    np.testing.assert_array_equal(s0, s1)
+    np.testing.assert_array_equal(t0, t1)
+    np.testing.assert_array_equal(p0, p1)
+    assert c1["nodes"] <= c0["nodes"] and c1["tris"] <= c0["tris"]
+    assert c1["max_stack"] <= 30
+
+
+@pytest.mark.parametrize("name", ["dodecahedron", "sphere16", "soup"])
+def test_reference_traversal_equals_brute_force(oracle, scenes, name):
+    tri, cam = {"dodecahedron": (scenes.dodecahedron(), scenes.pinhole_camera(aspect=1.0)),
+                "sphere16": (scenes.displaced_sphere(16), scenes.pinhole_camera()),
+                "soup": (scenes.random_soup(3000, size=0.05), scenes.pinhole_camera())}[name]
+    b = oracle.Bih(tri)
+    rays = _rays(oracle, scenes, cam, 128, 72)
+    t0, s0, _ = b.trace(rays, "ref")
+    t2, s2, _ = b.trace(rays, "brute")
+    np.testing.assert_array_equal(t0, t2)
+    np.testing.assert_array_equal(s0, s2)
+    assert 0.02 < (s0 >= 0).mean() < 0.98
+
+
+def test_flat_geometry_boundary_is_reference_behaviour(oracle, scenes):
+    """On axis-aligned walls the reference's strict comparisons drop hits brute force finds; the
+    pruned traversal must reproduce that, not 'fix' it (parity notes)."""
+    b = oracle.Bih(scenes.cornell_box())
+    rays = _rays(oracle, scenes, scenes.cornell_camera(), 256, 256)
+    t0, s0, _ = b.trace(rays, "ref")
+    t1, s1, _ = b.trace(rays, "proper")
+    t2, s2, _ = b.trace(rays, "brute")
+    np.testing.assert_array_equal(s0, s1)
+    assert (t0 != t2).sum() > 0           # the reference is not brute force here
+    assert np.all(t0 >= t2)               # it can only miss closer hits, never invent one
+
+
+def test_degenerate_inputs(oracle, scenes):
+    one = np.array([[0, 0, 0, 1, 0, 0, 0, 1, 0]], np.float32)
+    b = oracle.Bih(one)
+    assert b.nu == 1 and len(b.axis) == 0
+    rays = np.array([[0.2, 0.2, 1, 0, 0, -1], [0.2, 0.2, 1, 0, 0, 1], [5, 5, 1, 0, 0, -1]], np.float32)
+    t, s, p = b.trace(rays, "ref")
+    assert s.tolist() == [0, -1, -1] and t[0] == 1.0
+    # duplicates: identical triangles share a Morton cell; first slot wins ties
+    dup = np.repeat(scenes.dodecahedron(), 3, axis=0)
+    bd = oracle.Bih(dup)
+    assert bd.nu == 36 and np.all(bd.cnt == 3)
+    r2 = oracle.camera_rays(scenes.pinhole_camera(aspect=1.0), 32, 32)
+    t, s, p = bd.trace(r2, "ref")
+    hit = s >= 0
+    assert np.all(s[hit] % 3 == 0) and np.all(p[hit] % 3 == 0)   # stable sort keeps input order
+    # flat scene: zero extent on z -> NaN normalised centre -> cell 0 on that axis
+    flat = scenes.quad_grid([0, 0, 0], [1, 0, 0], [0, 1, 0], 8, 8)
+    bf = oracle.Bih(flat)
+    assert np.all(bf.codes & 0x09249249 == 0) and bf.nu > 1
+    # empty scene
+    be = oracle.Bih(np.zeros((0, 9), np.float32))
+    assert be.nu == 0
+    t, s, p = be.trace(rays, "ref")
+    assert np.all(s == -1)
+
+
+def test_det_threshold_constant():
+    """csrc/trace.cu compares det against 0x358637be in binary32 instead of (double)det < 0.000001
+    (R/src/CUDAKernels.cu:28); they must agree for every float."""
+    c = np.array([0x358637be], np.uint32).view(np.float32)[0]
+    for bits in range(0x358637be - 4, 0x358637be + 4):
+        d = np.array([bits], np.uint32).view(np.float32)[0]
+        assert (float(d) < 0.000001) == bool(d < c)
+    for d in np.float32([0.0, -1.0, 1e-7, 9.9e-7, 1e-6, 1.1e-6, 1.0]):
+        assert (float(d) < 0.000001) == bool(d < c)
+
+
+def test_reciprocal_double_rounding_is_innocuous():
+    """(float)(1.0 / (double)det) == correctly rounded binary32 reciprocal (trace.cu uses __frcp_rn)."""
+    rng = np.random.default_rng(1984)
+    det = np.exp(rng.uniform(np.log(1e-6), np.log(1e6), 200000)).astype(np.float32)
+    via_double = (1.0 / det.astype(np.float64)).astype(np.float32)
+    direct = (np.float32(1.0) / det).astype(np.float32)
+    np.testing.assert_array_equal(via_double, direct)
+
+
+def test_camera_rays_and_pack(oracle, scenes):
+    cam = scenes.reference_camera()
+    rays = oracle.camera_rays(cam, 8, 6, spp=3, jitter=True, seed=1984)
+    assert rays.shape == (8 * 6 * 3, 6) and np.all(rays[:, :3] == cam[:3])
+    again = oracle.camera_rays(cam, 8, 6, spp=3, jitter=True, seed=1984)
+    np.testing.assert_array_equal(rays, again)
+    centre = oracle.camera_rays(cam, 8, 6)
+    # pixel (0,0) centre: llc + (0.5/8)*hor + (0.5/6)*ver - origin
+    exp = cam[3:6] + np.float32(0.5 / 8) * cam[6:9] + np.float32(0.5 / 6) * cam[9:12] - cam[0:3]
+    np.testing.assert_allclose(centre[0, 3:], exp, rtol=1e-6)
+    fb = oracle.pack_framebuffer(np.array([3, -1, -1, -1], np.int32), 2, 1, 2)
+    # pixel 0: one hit one miss -> r=g=(255+20)/2=137.5 -> 137, b=20; pixel 1: miss -> (20,20,40)
+    assert fb.tolist() == [(20 << 16) | (137 << 8) | 137, (40 << 16) | (20 << 8) | 20]
