@@ -63,9 +63,9 @@ class BuildInfo(C.Structure):
 # every symbol include/bihrt.h declares (tests check that the library exports all of them)
 ABI_SYMBOLS = [
     "bihrt_version", "bihrt_create", "bihrt_destroy", "bihrt_last_error", "bihrt_set_stream", "bihrt_sync",
-    "bihrt_set_option", "bihrt_scene_load_triangles", "bihrt_scene_update_vertices", "bihrt_scene_load_obj",
+    "bihrt_set_option", "bihrt_get_stat", "bihrt_scene_load_triangles", "bihrt_scene_update_vertices", "bihrt_scene_load_obj",
     "bihrt_build", "bihrt_get_build_info", "bihrt_export_reference_view", "bihrt_trace", "bihrt_trace_counted",
-    "bihrt_render", "bihrt_render_shard", "bihrt_render_hits", "bihrt_framebuffer", "bihrt_framebuffer_read",
+    "bihrt_render", "bihrt_render_counted", "bihrt_render_shard", "bihrt_render_hits", "bihrt_framebuffer", "bihrt_framebuffer_read",
     "bihrt_bih_blob_bytes", "bihrt_bih_export", "bihrt_bih_import",
 ]
 
@@ -143,6 +143,11 @@ class Renderer:
 
     def set_option(self, name, value):
         self._check(self._lib.bihrt_set_option(self._ctx, name.encode(), C.c_int64(int(value))))
+
+    def get_stat(self, name):
+        v = C.c_int64()
+        self._check(self._lib.bihrt_get_stat(self._ctx, name.encode(), C.byref(v)))
+        return v.value
 
     # -- App::LoadModels ------------------------------------------------------------------------
     def load_models(self, src):
@@ -235,6 +240,13 @@ class Renderer:
                                                  C.c_uint64(seed), C.c_uint32(RENDER_JITTER if jitter else 0),
                                                  C.c_int32(shard[0]), C.c_int32(shard[1])))
         return self
+
+    def render_counted(self, camera, w, h, spp=1, seed=1984, jitter=False):
+        cam = camera if isinstance(camera, Camera) else Camera.from_array(camera)
+        cnt = (C.c_uint64 * 4)()
+        self._check(self._lib.bihrt_render_counted(self._ctx, C.byref(cam), C.c_int32(w), C.c_int32(h), C.c_int32(spp),
+                                                   C.c_uint64(seed), C.c_uint32(RENDER_JITTER if jitter else 0), cnt))
+        return {"nodes": cnt[0], "tris": cnt[1], "max_stack": cnt[2], "rays": cnt[3]}
 
     def render_hits(self, camera, w, h, spp=1, seed=1984, jitter=False):
         cam = camera if isinstance(camera, Camera) else Camera.from_array(camera)

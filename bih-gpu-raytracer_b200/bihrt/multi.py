@@ -1,0 +1,69 @@
+"""Multi-GPU plumbing: one process per GPU, torch.distributed for the two collectives the path has.
+
+The reference is single-GPU (no NCCL/MPI/peer copies).  Rays are independent given a
+replicated tree, so the partition is data-parallel:
+
+  * the BIH is built once on rank `src` and replicated with ONE broadcast of the blob
+    [header | nodes | leaf-ordered triangles] (bihrt_bih_export / bihrt_bih_import);
+  * the image's 32x32-pixel tiles are dealt round-robin (tile k -> rank k mod G), each rank renders
+    only its tiles (bihrt_render_shard) and leaves the other pixels 0;
+  * the framebuffer is gathered at the end with ONE reduce (SUM of disjoint shards == gather).
+
+No collective runs during traversal.  The helpers take any torch.distributed backend so the same code
+is exercised with gloo on CPU tensors in tests/test_distributed.py.
+"""
+import numpy as np
+
+TILE = 32
+
+
+def tile_owner(w, h, world):
+    """(h, w) int32 array: rank that renders each pixel (tile id = ty * tiles_x + tx, id mod world)."""
+    tx = (w + TILE - 1) // TILE
+    jj, ii = np.meshgrid(np.arange(h) // TILE, np.arange(w) // TILE, indexing="ij")
+    return ((jj * tx + ii) % world).astype(np.int32)
+
+
+def shard_ray_count(w, h, spp, rank, world):
+    return int((tile_owner(w, h, world) == rank).sum()) * spp
+
+
+class _CudaView:
+    """Zero-copy torch view of a device pointer owned by the library (via __cuda_array_interface__)."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def framebuffer_tensor(renderer):
+    """The context's framebuffer (Renderer::m_cudaDestResource) as a (h, w) int32 CUDA tensor, no copy."""
+    import torch
+    ptr, w, h = renderer.framebuffer_ptr()
+    return torch.as_tensor(_CudaView(ptr, (h, w), "<i4"), device="cuda:%d" % renderer.device)
+
+
+def replicate_bih(renderer, dist, src=0, device=None):
+    """Broadcast the BIH built on rank `src` to every rank (one collective).  Returns the blob size."""
+    import torch
+    rank = dist.get_rank()
+    dev = device if device is not None else "cuda:%d" % renderer.device
+    size = torch.zeros(1, dtype=torch.int64, device=dev)
+    if rank == src:
+        size[0] = renderer.bih_blob_bytes()
+    dist.broadcast(size, src=src)
+    nbytes = int(size.item())
+    blob = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    if rank == src:
+        renderer.bih_export(blob, nbytes)
+        renderer.sync()
+    dist.broadcast(blob, src=src)
+    if rank != src:
+        renderer.bih_import(blob, nbytes)
+        renderer.sync()
+    return nbytes
+
+
+def gather_framebuffer(fb, dist, dst=0):
+    """Combine the ranks' disjoint shards (0 outside a rank's tiles) on rank `dst`: one reduce."""
+    dist.reduce(fb, dst=dst, op=dist.ReduceOp.SUM)
+    return fb

@@ -159,6 +159,13 @@ int bihrt_set_option(bihrt_ctx* c, const char* name, int64_t v) {
     return BIHRT_OK;
 }
 
+int bihrt_get_stat(bihrt_ctx* c, const char* name, int64_t* v) {
+    if (!c || !name || !v) return BIHRT_ERR_INVALID;
+    if (!strcmp(name, "kernel_launches")) *v = c->kernel_launches;
+    else return bihrt_fail(c, BIHRT_ERR_INVALID, "unknown stat '%s'", name);
+    return BIHRT_OK;
+}
+
 // ---- scene load ------------------------------------------------------------------------------
 static int upload_triangles(bihrt_ctx* c, const float* xyz9, int64_t n) {
     if (n > 0) {
@@ -399,8 +406,8 @@ static int render_check(bihrt_ctx* c, const bihrt_camera* cam, int w, int h, int
     return BIHRT_OK;
 }
 
-int bihrt_render_shard(bihrt_ctx* c, const bihrt_camera* cam, int32_t w, int32_t h, int32_t spp, uint64_t seed, uint32_t flags,
-                       int32_t shard_index, int32_t shard_count) {
+static int render_impl(bihrt_ctx* c, const bihrt_camera* cam, int32_t w, int32_t h, int32_t spp, uint64_t seed, uint32_t flags,
+                       int32_t shard_index, int32_t shard_count, uint64_t* counters) {
     ENTER(c);
     int rc = render_check(c, cam, w, h, spp, shard_index, shard_count);
     if (rc) return rc;
@@ -411,7 +418,25 @@ int bihrt_render_shard(bihrt_ctx* c, const bihrt_camera* cam, int32_t w, int32_t
     TraceArgs a; base_args(c, a);
     a.cam = *cam; a.w = w; a.h = h; a.spp = spp; a.seed = seed; a.flags = flags;
     a.shard_index = shard_index; a.shard_count = shard_count; a.fb = c->d_fb;
-    return bihrt_trace_launch(c, a, 1, false);
+    if (!counters) return bihrt_trace_launch(c, a, 1, false);
+    BIHRT_CUDA(c, cudaMemsetAsync(c->d_counters, 0, 32, c->stream));
+    if ((rc = bihrt_trace_launch(c, a, 1, true))) return rc;
+    unsigned long long hc[4];
+    BIHRT_CUDA(c, cudaMemcpyAsync(hc, c->d_counters, 32, cudaMemcpyDeviceToHost, c->stream));
+    BIHRT_CUDA(c, cudaStreamSynchronize(c->stream));
+    counters[0] = hc[0]; counters[1] = hc[1]; counters[2] = hc[2]; counters[3] = (uint64_t)w * h * spp;
+    return BIHRT_OK;
+}
+
+int bihrt_render_shard(bihrt_ctx* c, const bihrt_camera* cam, int32_t w, int32_t h, int32_t spp, uint64_t seed, uint32_t flags,
+                       int32_t shard_index, int32_t shard_count) {
+    return render_impl(c, cam, w, h, spp, seed, flags, shard_index, shard_count, nullptr);
+}
+
+int bihrt_render_counted(bihrt_ctx* c, const bihrt_camera* cam, int32_t w, int32_t h, int32_t spp, uint64_t seed, uint32_t flags,
+                         uint64_t counters[4]) {
+    if (!counters) return BIHRT_ERR_INVALID;
+    return render_impl(c, cam, w, h, spp, seed, flags, 0, 1, counters);
 }
 
 int bihrt_render(bihrt_ctx* c, const bihrt_camera* cam, int32_t w, int32_t h, int32_t spp, uint64_t seed, uint32_t flags) {

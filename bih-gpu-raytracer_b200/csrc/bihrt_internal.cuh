@@ -97,6 +97,7 @@ struct bihrt_ctx {
     int opt_trace_blocks_per_sm = 0;   // 0 = occupancy query
     int opt_trace_variant = 0;
     int opt_sort_passes = 4;
+    int64_t kernel_launches = 0;
 };
 
 int  bihrt_fail(bihrt_ctx* c, int code, const char* fmt, ...);

@@ -486,6 +486,7 @@ int bihrt_build_launch(bihrt_ctx* c) {
                                      c->d_lookback + (size_t)4 * os_tiles * 256, c->d_hdr);
     k_tree<<<(n + 127) / 128, 128, 0, st>>>(c->d_tri_in, c->d_vals[cur], c->d_umc, c->d_first, c->d_hdr, c->d_nodes, c->d_tris,
                                             c->d_arrive, reinterpret_cast<float4*>(c->d_boxscratch));
+    c->kernel_launches += 9;    // k_init, k_scene_box, k_morton, 4 x k_onesweep, k_rle, k_tree
     BIHRT_CUDA(c, cudaGetLastError());
     return BIHRT_OK;
 }

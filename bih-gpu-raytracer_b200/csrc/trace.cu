@@ -276,6 +276,7 @@ static int launch(bihrt_ctx* c, const TraceArgs& a) {
     }
     BIHRT_CUDA(c, cudaMemsetAsync(a.work, 0, 4, c->stream));
     k_trace<MODE, COUNTED><<<c->sm_count * per_sm, 128, 0, c->stream>>>(a);
+    c->kernel_launches += 1;
     BIHRT_CUDA(c, cudaGetLastError());
     return BIHRT_OK;
 }

@@ -108,6 +108,7 @@ BIHRT_API const char* bihrt_last_error(const bihrt_ctx* ctx);                   
 BIHRT_API int         bihrt_set_stream(bihrt_ctx* ctx, void* cuda_stream);      /* run on a caller-owned stream (NULL = own stream) */
 BIHRT_API int         bihrt_sync(bihrt_ctx* ctx);                               /* replaces the cudaDeviceSynchronize after each step, R/src/Renderer.cpp:428-503 */
 BIHRT_API int         bihrt_set_option(bihrt_ctx* ctx, const char* name, int64_t value);  /* tuning knobs, see DESIGN.md */
+BIHRT_API int         bihrt_get_stat(bihrt_ctx* ctx, const char* name, int64_t* value);   /* "kernel_launches": kernels of this library launched so far */
 
 /* ---- scene load: App::LoadModels + GPUArrayManager::Allocate*, R/src/App.cpp:65-167,
  *      R/src/GPUArrayManager.cpp:7-91.  xyz9 = n x (v0,v1,v2) floats in model->mesh->face order,
@@ -139,6 +140,9 @@ BIHRT_API int bihrt_trace_counted(bihrt_ctx* ctx, const bihrt_ray* rays, int64_t
  * (seed, pixel, sample) instead of per-pixel XORWOW state (documented difference). */
 BIHRT_API int bihrt_render(bihrt_ctx* ctx, const bihrt_camera* cam, int32_t w, int32_t h, int32_t spp,
                  uint64_t seed, uint32_t flags);
+/* Same as bihrt_render through the instrumented kernel: counters as in bihrt_trace_counted. */
+BIHRT_API int bihrt_render_counted(bihrt_ctx* ctx, const bihrt_camera* cam, int32_t w, int32_t h, int32_t spp,
+                         uint64_t seed, uint32_t flags, uint64_t counters[4]);
 /* Multi-GPU: render only the 32x32-pixel tiles with tile_id % shard_count == shard_index; every
  * other pixel of the framebuffer is set to 0, so a sum (or bitwise OR) of the shards' framebuffers
  * is the full image. */
