@@ -155,6 +155,11 @@ int bihrt_set_option(bihrt_ctx* c, const char* name, int64_t v) {
     if (!c || !name) return BIHRT_ERR_INVALID;
     if (!strcmp(name, "trace_blocks_per_sm")) c->opt_trace_blocks_per_sm = (int)v;
     else if (!strcmp(name, "trace_variant")) c->opt_trace_variant = (int)v;
+    else if (!strcmp(name, "trace_refill_threshold")) c->opt_refill_threshold = (int)std::max<int64_t>(1, std::min<int64_t>(32, v));
+    else if (!strcmp(name, "trace_vote")) c->opt_vote = (int)v;
+    else if (!strcmp(name, "trace_leaf_votes")) c->opt_leaf_votes = (int)v;
+    else if (!strcmp(name, "trace_speculate")) c->opt_speculate = (int)v;
+    else if (!strcmp(name, "trace_chunk_items")) c->opt_chunk_items = (int)std::max<int64_t>(32, (v + 31) / 32 * 32);
     else return bihrt_fail(c, BIHRT_ERR_INVALID, "unknown option '%s'", name);
     return BIHRT_OK;
 }
@@ -178,7 +183,7 @@ static int upload_triangles(bihrt_ctx* c, const float* xyz9, int64_t n) {
 int bihrt_scene_load_triangles(bihrt_ctx* c, const float* xyz9, int64_t n) {
     ENTER(c);
     if (n < 0 || (n > 0 && !xyz9)) return bihrt_fail(c, BIHRT_ERR_INVALID, "bad triangle array");
-    if (n >= (1ll << 30)) return bihrt_fail(c, BIHRT_ERR_INVALID, "at most 2^30-1 triangles (30-bit child references)");
+    if (n >= BIH_MAX_TRIS) return bihrt_fail(c, BIHRT_ERR_INVALID, "at most 2^29-1 triangles (29-bit child references)");
     int rc = ensure_capacity(c, n, true);
     if (rc) return rc;
     c->n = n; c->have_scene = true; c->built = false;
@@ -302,6 +307,7 @@ int bihrt_export_reference_view(bihrt_ctx* c, bihrt_refview* v) {
         if (v->leaf_parents) v->leaf_parents[k] = -1;
     }
     for (size_t i = 0; i < ni; i++) if (v->parent) v->parent[i] = -1;
+    if (v->axis && ni) v->axis[0] = (int32_t)h.root_axis;
     for (size_t i = 0; i < ni; i++) {
         const BihNode& nd = nodes[i];
         const bool ll = nd.ref_l & BIH_REF_LEAF, rl = nd.ref_r & BIH_REF_LEAF;
@@ -311,7 +317,10 @@ int bihrt_export_reference_view(bihrt_ctx* c, bihrt_refview* v) {
         else if (!rl) split = ir - 1;
         else split = (uint32_t)(std::lower_bound(first.begin(), first.begin() + nu, il) - first.begin());   // leaf whose first slot is il
         if (v->clip_planes) { v->clip_planes[2 * i] = nd.clip0; v->clip_planes[2 * i + 1] = nd.clip1; }
-        if (v->axis) v->axis[i] = (int32_t)(((nd.ref_l >> 30) & 1u) | ((nd.ref_r >> 29) & 2u));
+        if (v->axis) {      // a node's axis is stored in its parent's reference to it
+            if (!ll) v->axis[split] = (int32_t)((nd.ref_l >> BIH_REF_AXIS_SHIFT) & 3u);
+            if (!rl) v->axis[split + 1] = (int32_t)((nd.ref_r >> BIH_REF_AXIS_SHIFT) & 3u);
+        }
         if (v->is_leaf) { v->is_leaf[2 * i] = ll; v->is_leaf[2 * i + 1] = rl; }
         if (v->children) { v->children[2 * i] = (int32_t)split; v->children[2 * i + 1] = (int32_t)split + 1; }
         if (ll) { if (v->leaf_parents) v->leaf_parents[split] = (int32_t)i; } else if (v->parent) v->parent[split] = (int32_t)i;
@@ -335,6 +344,8 @@ static void base_args(bihrt_ctx* c, TraceArgs& a) {
     a.hdr = c->d_hdr; a.nodes = c->d_nodes; a.tris = c->d_tris;
     a.counters = c->d_counters; a.work = c->d_work;
     a.shard_index = 0; a.shard_count = 1;
+    a.refill_threshold = c->opt_refill_threshold; a.chunk_items = c->opt_chunk_items;
+    a.vote = c->opt_vote; a.leaf_votes = c->opt_leaf_votes; a.speculate = c->opt_speculate;
 }
 
 // outputs may individually be host or device; host ones are staged through d_io
@@ -368,7 +379,7 @@ static int trace_impl(bihrt_ctx* c, const bihrt_ray* rays, int64_t n, float* t, 
     ENTER(c);
     if (!c->built) return bihrt_fail(c, BIHRT_ERR_STATE, "BIH not built");
     if (n < 0 || (n > 0 && !rays)) return bihrt_fail(c, BIHRT_ERR_INVALID, "bad ray array");
-    if (n >= (1ll << 36)) return bihrt_fail(c, BIHRT_ERR_INVALID, "too many rays in one call");
+    if (n >= (1ll << 32) - (1ll << 24)) return bihrt_fail(c, BIHRT_ERR_INVALID, "too many rays in one call (32-bit work counter)");
     if (counters) BIHRT_CUDA(c, cudaMemsetAsync(c->d_counters, 0, 32, c->stream));
     if (n > 0) {
         const bool rays_dev = is_device_ptr(rays);
@@ -401,7 +412,8 @@ int bihrt_trace_counted(bihrt_ctx* c, const bihrt_ray* rays, int64_t n, float* t
 
 static int render_check(bihrt_ctx* c, const bihrt_camera* cam, int w, int h, int spp, int si, int sc) {
     if (!c->built) return bihrt_fail(c, BIHRT_ERR_STATE, "BIH not built");
-    if (!cam || w <= 0 || h <= 0 || spp <= 0 || (int64_t)w * h >= (1ll << 31)) return bihrt_fail(c, BIHRT_ERR_INVALID, "bad render arguments");
+    if (!cam || w <= 0 || h <= 0 || spp <= 0 || w > 65535 || h > 65535 || (int64_t)w * h >= (1ll << 31) - (1ll << 24))
+        return bihrt_fail(c, BIHRT_ERR_INVALID, "bad render arguments");
     if (sc < 1 || si < 0 || si >= sc) return bihrt_fail(c, BIHRT_ERR_INVALID, "bad shard %d of %d", si, sc);
     return BIHRT_OK;
 }

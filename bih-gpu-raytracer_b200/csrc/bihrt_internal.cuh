@@ -10,9 +10,11 @@
 // -------------------------------------------------------------------------------------------
 // Node, 16 B, one LDG.128 per visit.  Index = the reference's (Karras) node index, so node i here is
 // TreeInternalNode i of R/src/Tree.cuh:16-24.  A child reference packs
-//   bit 31    : child is a leaf
-//   bit 30    : one bit of the split axis (ref_l: axis&1, ref_r: axis>>1)
-//   bits 29..0: internal child -> node index; leaf child -> first slot of the leaf in tris[]
+//   bit 31     : child is a leaf
+//   bits 30..29: split axis OF THE CHILD (internal children; 0 for leaves) -- the traversal knows the
+//                axis of a node before it fetches it, so the ray constants for that axis are loaded
+//                in parallel with the node instead of after it.  The root's axis is in the header.
+//   bits 28..0 : internal child -> node index; leaf child -> first slot of the leaf in tris[]
 struct __align__(16) BihNode {
     float    clip0;   // max over the left subtree of hi[axis]   (t_clipPlanes[0])
     float    clip1;   // min over the right subtree of lo[axis]  (t_clipPlanes[1])
@@ -20,8 +22,9 @@ struct __align__(16) BihNode {
     uint32_t ref_r;
 };
 #define BIH_REF_LEAF  0x80000000u
-#define BIH_REF_AXIS  0x40000000u
-#define BIH_REF_INDEX 0x3FFFFFFFu
+#define BIH_REF_AXIS_SHIFT 29
+#define BIH_REF_INDEX 0x1FFFFFFFu
+#define BIH_MAX_TRIS  (1ll << 29)
 
 // Leaf-ordered triangle, 48 B = 3 x LDG.128: v0, e1 = v1 - v0, e2 = v2 - v0 (the two edges
 // RayTriangleIntersection recomputes per test, R/src/CUDAKernels.cu:18-19), the input triangle index
@@ -46,7 +49,8 @@ struct BihHeader {
     float    lo[3];      // scene box
     float    hi[3];
     uint32_t status;     // 0 ok, !=0 device watchdog
-    uint32_t pad[7];
+    uint32_t root_axis;  // split axis of node 0
+    uint32_t pad[6];
 };
 static_assert(sizeof(BihHeader) == 64, "header is one 64-byte line");
 
@@ -96,6 +100,9 @@ struct bihrt_ctx {
     int opt_trace_block = 128;
     int opt_trace_blocks_per_sm = 0;   // 0 = occupancy query
     int opt_trace_variant = 0;
+    int opt_refill_threshold = 32;
+    int opt_chunk_items = 32;
+    int opt_vote = 0, opt_leaf_votes = 16, opt_speculate = 0;
     int opt_sort_passes = 4;
     int64_t kernel_launches = 0;
 };
@@ -115,6 +122,11 @@ struct TraceArgs {
     bihrt_camera cam; int w, h, spp; uint64_t seed; uint32_t flags; int shard_index, shard_count;
     uint32_t* fb;
     unsigned long long* counters; uint32_t* work;
+    int refill_threshold;   // lanes whose ray ended wait until this many are idle (or nobody is busy)
+    int chunk_items;        // work items (rays / pixels) a warp takes from the global counter at once
+    int vote;               // 0: node phase ends when no lane has a node; 1: ... or leaf_votes lanes wait; 2: ... or waiters > walkers
+    int leaf_votes;
+    int speculate;          // park one leaf and keep walking
 };
 int bihrt_trace_launch(bihrt_ctx* c, const TraceArgs& a, int mode /*0 rays,1 render fb,2 render hits*/, bool counted);
 

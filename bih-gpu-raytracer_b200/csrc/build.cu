@@ -70,7 +70,7 @@ __device__ __forceinline__ void minmax3(float a, float b, float c, float& mn, fl
 __global__ void k_init(uint32_t* hist, uint32_t* enc, BihHeader* hdr, uint32_t n) {
     for (int i = threadIdx.x; i < H_WORDS; i += blockDim.x) hist[i] = 0;
     if (threadIdx.x < 3) { enc[threadIdx.x] = 0xFFFFFFFFu; enc[3 + threadIdx.x] = 0u; }
-    if (threadIdx.x == 0) { hdr->n = n; hdr->nu = 0; hdr->status = 0; }
+    if (threadIdx.x == 0) { hdr->n = n; hdr->nu = 0; hdr->status = 0; hdr->root_axis = 0; }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -371,7 +371,7 @@ __device__ __forceinline__ float pick(const float v[3], int axis) { return axis 
 
 __global__ void __launch_bounds__(128) k_tree(const float* __restrict__ tri_in, const uint32_t* __restrict__ idx_sorted,
                                               const uint32_t* __restrict__ umc, const uint32_t* __restrict__ first,
-                                              const BihHeader* __restrict__ hdr, BihNode* __restrict__ nodes,
+                                              BihHeader* hdr, BihNode* __restrict__ nodes,
                                               BihTri* __restrict__ tris, int32_t* __restrict__ arrive,
                                               float4* __restrict__ boxscratch) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -444,10 +444,13 @@ __global__ void __launch_bounds__(128) k_tree(const float* __restrict__ tri_in, 
         const int axis = (__clz(umc[ps] ^ umc[ps + 1]) + 1) % 3;    // R/src/CUDAKernels.cu:702-706
         cl0 = pick(lbox.hi, axis);
         cl1 = pick(rbox.lo, axis);
-        ref_l = (a == ps) ? (BIH_REF_LEAF | first[ps]) : ps;
-        ref_r = (ps + 1 == b) ? (BIH_REF_LEAF | first[ps + 1]) : (ps + 1);
-        if (axis & 1) ref_l |= BIH_REF_AXIS;
-        if (axis & 2) ref_r |= BIH_REF_AXIS;
+        // a radix-tree node over leaves [l,r] splits on the first bit in which umc[l] and umc[r] differ,
+        // so a child's axis follows from its range ends (== (lcp(children of the child) + 1) % 3)
+        ref_l = (a == ps) ? (BIH_REF_LEAF | first[ps])
+                          : (ps | ((uint32_t)((__clz(umc[a] ^ umc[ps]) + 1) % 3) << BIH_REF_AXIS_SHIFT));
+        ref_r = (ps + 1 == b) ? (BIH_REF_LEAF | first[ps + 1])
+                              : ((ps + 1) | ((uint32_t)((__clz(umc[ps + 1] ^ umc[b]) + 1) % 3) << BIH_REF_AXIS_SHIFT));
+        if (a == 0 && b == nu - 1) hdr->root_axis = (uint32_t)axis;
         Box u;
 #pragma unroll
         for (int i = 0; i < 3; i++) { u.lo[i] = fminf(lbox.lo[i], rbox.lo[i]); u.hi[i] = fmaxf(lbox.hi[i], rbox.hi[i]); }

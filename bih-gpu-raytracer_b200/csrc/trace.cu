@@ -2,65 +2,62 @@
 // FindNearestTriangle / RayTriangleIntersection (R/src/CUDAKernels.cu:17-50,206-423) and
 // Camera::GetRay / Ray::Ray (R/src/Camera.cu:18-20, R/src/Ray.cu:3-10).
 //
-// Kernel shape: persistent warps (grid = SMs x resident blocks) pull 32-ray packets -- 8x4 pixel
-// tiles for camera rays -- from one atomic counter; every lane walks its own ray with a 16-byte
-// per-entry stack; nodes (16 B) and leaf-ordered triangles (3 x 16 B) are fetched with single
-// 128-bit read-only loads.  The walk is a two-phase ("while-while") loop: lanes step through
-// internal nodes until they hold a leaf to test, the warp re-converges, leaves are tested, repeat.
+// Kernel shape
+//   * persistent warps (grid = SMs x resident blocks); a warp takes chunks of work items (rays, or
+//     pixels in 8x4-tile order) from one global atomic counter and hands them to its lanes one at a
+//     time: a lane whose ray has ended does not wait for the other 31 -- once `refill_threshold`
+//     lanes are idle (or nobody is busy) they are given their next sample / pixel / ray together;
+//   * every lane walks its own ray with a short stack of 16-byte items (child reference + the three
+//     interval bounds) in local memory; a leaf is an item like a node, so the hot loop has one shape;
+//   * nodes (16 B) and leaf-ordered triangles (3 x 16 B) are fetched with single 128-bit read-only
+//     loads; the per-axis ray constants (origin, 1/dir) sit in shared memory and are picked with the
+//     node's axis bits by one 64-bit LDS instead of a select chain;
+//   * two-phase ("while-while") loop: lanes step through internal nodes until they hold a leaf, the
+//     warp re-converges, leaves are tested, repeat; a vote ends the node phase early when most lanes
+//     already wait with a leaf, and a lane may park one leaf and keep walking (speculation).
 //
-// Logical per-ray algorithm = oracle/bih_oracle.c:traverse_proper (pruned traversal that returns
-// what the reference's TraverseTree returns, including on axis-aligned flat geometry where the
-// reference's strict comparisons decide).  Arithmetic is IEEE binary32 without FMA contraction
-// (explicit __f*_rn) so t is bit-identical to the oracle's.
+// Logical per-ray algorithm = oracle/bih_oracle.c:traverse_proper (pruned traversal that returns what
+// the reference's TraverseTree returns, including on axis-aligned flat geometry where the reference's
+// strict comparisons decide).  Arithmetic is IEEE binary32 without FMA contraction (explicit __f*_rn)
+// so t is bit-identical to the oracle's.
 #include "bihrt_internal.cuh"
 #include <float.h>
 
 #define FULL 0xffffffffu
-#define STACK_DEPTH 32          // <= 30 pushes possible: one per Morton bit on a root-to-leaf path
-#define NO_NODE 0xFFFFFFFFu
+#define STACK_DEPTH 32          // <= 31 items: one per Morton bit on a root-to-leaf path, plus one
+#define NONE 0xFFFFFFFFu        // "no item": leaf bit set, never a valid slot
+#define TRACE_THREADS 128
 
 // (double)det < 0.000001 (R/src/CUDAKernels.cu:28)  <=>  det < 0x358637be as binary32
 #define DET_EPS __uint_as_float(0x358637beu)
 
-struct Ray {
-    float ox, oy, oz, dx, dy, dz, ix, iy, iz;
-    uint32_t sign;   // bit k: invDir[k] < 0
-};
-
-__device__ __forceinline__ Ray make_ray(float ox, float oy, float oz, float dx, float dy, float dz) {
-    Ray r;
-    r.ox = ox; r.oy = oy; r.oz = oz; r.dx = dx; r.dy = dy; r.dz = dz;
-    r.ix = __frcp_rn(dx); r.iy = __frcp_rn(dy); r.iz = __frcp_rn(dz);      // 1 / b, R/src/Ray.cu:6
-    r.sign = (r.ix < 0.f ? 1u : 0u) | (r.iy < 0.f ? 2u : 0u) | (r.iz < 0.f ? 4u : 0u);
-    return r;
-}
-
-struct Hit { float t; int slot; uint32_t prim; };
+struct Hit { float t; int slot; };
 
 template <bool COUNTED>
-__device__ __forceinline__ void test_leaf(const BihTri* __restrict__ tris, uint32_t slot, const Ray& r, Hit& h, uint32_t& ntris) {
+__device__ __forceinline__ void test_leaf(const BihTri* __restrict__ tris, uint32_t slot, float ox, float oy, float oz,
+                                          float dx, float dy, float dz, Hit& h, uint32_t& ntris) {
     for (;;) {
         const float4* p = reinterpret_cast<const float4*>(tris + slot);
         const float4 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2);
         if (COUNTED) ntris++;
         const float e1x = q0.w, e1y = q1.x, e1z = q1.y, e2x = q1.z, e2y = q1.w, e2z = q2.x;
-        // pvec = cross(dir, e2)
-        const float px = __fsub_rn(__fmul_rn(r.dy, e2z), __fmul_rn(e2y, r.dz));
-        const float py = __fsub_rn(__fmul_rn(r.dz, e2x), __fmul_rn(e2z, r.dx));
-        const float pz = __fsub_rn(__fmul_rn(r.dx, e2y), __fmul_rn(e2x, r.dy));
+        // pvec = cross(dir, e2); det = dot(e1, pvec)                       R/src/CUDAKernels.cu:24-26
+        const float px = __fsub_rn(__fmul_rn(dy, e2z), __fmul_rn(e2y, dz));
+        const float py = __fsub_rn(__fmul_rn(dz, e2x), __fmul_rn(e2z, dx));
+        const float pz = __fsub_rn(__fmul_rn(dx, e2y), __fmul_rn(e2x, dy));
         const float det = __fadd_rn(__fadd_rn(__fmul_rn(e1x, px), __fmul_rn(e1y, py)), __fmul_rn(e1z, pz));
         if (!(det < DET_EPS)) {
             const float inv = __frcp_rn(det);        // == (float)(1.0 / (double)det), :31 (53 >= 2*24+2 bits)
-            const float tx = __fsub_rn(r.ox, q0.x), ty = __fsub_rn(r.oy, q0.y), tz = __fsub_rn(r.oz, q0.z);
+            const float tx = __fsub_rn(ox, q0.x), ty = __fsub_rn(oy, q0.y), tz = __fsub_rn(oz, q0.z);
             const float u = __fmul_rn(__fadd_rn(__fadd_rn(__fmul_rn(tx, px), __fmul_rn(ty, py)), __fmul_rn(tz, pz)), inv);
             if (!(u < 0.f || u > 1.f)) {
                 const float qx = __fsub_rn(__fmul_rn(ty, e1z), __fmul_rn(e1y, tz));
                 const float qy = __fsub_rn(__fmul_rn(tz, e1x), __fmul_rn(e1z, tx));
                 const float qz = __fsub_rn(__fmul_rn(tx, e1y), __fmul_rn(e1x, ty));
-                const float v = __fmul_rn(__fadd_rn(__fadd_rn(__fmul_rn(r.dx, qx), __fmul_rn(r.dy, qy)), __fmul_rn(r.dz, qz)), inv);
+                const float v = __fmul_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, qx), __fmul_rn(dy, qy)), __fmul_rn(dz, qz)), inv);
                 if (!(v < 0.f || __fadd_rn(u, v) > 1.f)) {
                     const float t = __fmul_rn(__fadd_rn(__fadd_rn(__fmul_rn(e2x, qx), __fmul_rn(e2y, qy)), __fmul_rn(e2z, qz)), inv);
-                    if (t > 0.f && t < h.t) { h.t = t; h.slot = (int)slot; h.prim = __float_as_uint(q2.y); }
+                    if (t > 0.f && t < h.t) { h.t = t; h.slot = (int)slot; }      // :218-221, slot = sorted index
                 }
             }
         }
@@ -69,189 +66,241 @@ __device__ __forceinline__ void test_leaf(const BihTri* __restrict__ tris, uint3
     }
 }
 
-// slab test against the scene box, R/src/CUDAKernels.cu:237-262 (same operation order)
-__device__ __forceinline__ bool scene_slab(const float lo[3], const float hi[3], const Ray& r, float& tMin, float& tMax) {
-    const float nx = (r.sign & 1u) ? hi[0] : lo[0], fx = (r.sign & 1u) ? lo[0] : hi[0];
-    const float ny = (r.sign & 2u) ? hi[1] : lo[1], fy = (r.sign & 2u) ? lo[1] : hi[1];
-    const float nz = (r.sign & 4u) ? hi[2] : lo[2], fz = (r.sign & 4u) ? lo[2] : hi[2];
-    tMin = __fmul_rn(__fsub_rn(nx, r.ox), r.ix);
-    tMax = __fmul_rn(__fsub_rn(fx, r.ox), r.ix);
-    const float tymin = __fmul_rn(__fsub_rn(ny, r.oy), r.iy);
-    const float tymax = __fmul_rn(__fsub_rn(fy, r.oy), r.iy);
-    if ((tMin > tymax) || (tymin > tMax)) return false;
-    if (tymin > tMin) tMin = tymin;
-    if (tymax < tMax) tMax = tymax;
-    const float tzmin = __fmul_rn(__fsub_rn(nz, r.oz), r.iz);
-    const float tzmax = __fmul_rn(__fsub_rn(fz, r.oz), r.iz);
-    if ((tMin > tzmax) || (tzmin > tMax)) return false;
-    if (tzmin > tMin) tMin = tzmin;
-    if (tzmax < tMax) tMax = tzmax;
-    return true;
-}
+// ------------------------------------------------------------------------------------------
+// MODE 0: ray list -> (t, slot, prim);  1: camera -> packed framebuffer;  2: camera -> per-sample hits
+// Work item = one ray (MODE 0) or one pixel with its spp samples (MODE 1/2).
+// ------------------------------------------------------------------------------------------
+template <int MODE, bool COUNTED>
+__global__ void __launch_bounds__(TRACE_THREADS) k_trace(TraceArgs a) {
+    // per-axis ray constants (origin, 1/dir), one row of 3 float2 per thread: 24-byte stride keeps a
+    // half-warp's 64-bit accesses on distinct banks when the lanes agree on the axis
+    __shared__ float2 s_ray[TRACE_THREADS * 3];
+    const int lane = threadIdx.x & 31;
+    const uint32_t lt = (1u << lane) - 1u;
+    float2* my_ray = s_ray + threadIdx.x * 3;
+    const BihNode* __restrict__ nodes = a.nodes;
+    const BihTri* __restrict__ tris = a.tris;
+    const uint32_t nu = a.hdr->nu;
+    const float blo[3] = { a.hdr->lo[0], a.hdr->lo[1], a.hdr->lo[2] }, bhi[3] = { a.hdr->hi[0], a.hdr->hi[1], a.hdr->hi[2] };
+    uint32_t nnodes = 0, ntris = 0, maxsp = 0;
 
-// One ray.  `active` lanes of the warp call this together (inactive lanes pass active=false and
-// only take part in the warp-level re-convergence).
-template <bool COUNTED>
-__device__ __forceinline__ void trace_ray(const BihNode* __restrict__ nodes, const BihTri* __restrict__ tris,
-                                          uint32_t nu, const float lo[3], const float hi[3], bool active,
-                                          const Ray& r, Hit& h, uint32_t& nnodes, uint32_t& ntris, uint32_t& maxsp) {
-    h.t = FLT_MAX; h.slot = -1; h.prim = 0xFFFFFFFFu;
-    float rMin = 0.f, pMin = 0.f, pMax = 0.f;
-    uint32_t cur = NO_NODE;
-    if (active && nu > 0) {
-        float sMax;
-        if (scene_slab(lo, hi, r, rMin, sMax)) {
-            if (nu == 1) { test_leaf<COUNTED>(tris, 0, r, h, ntris); }
-            else { cur = 0; pMin = fmaxf(rMin, 0.f); pMax = sMax; }
-        }
+    // work items
+    uint64_t total;
+    int tx = 1;
+    if (MODE == 0) total = (uint64_t)a.nrays;
+    else {
+        tx = (a.w + 31) / 32;
+        const int ty = (a.h + 31) / 32, T = tx * ty;
+        const int my_tiles = T > a.shard_index ? (T - a.shard_index + a.shard_count - 1) / a.shard_count : 0;
+        total = (uint64_t)my_tiles * 1024u;
     }
+    const int nsamp = MODE == 0 ? 1 : a.spp;
+    uint64_t pool_next = 0, pool_end = 0;      // warp-uniform
+    bool exhausted = false;                    // warp-uniform: the global counter ran past `total`
+
+    // lane state
+    uint64_t item = ~0ull;                     // current work item, ~0 = none
+    int s = 0;                                 // sample of the item being traced
+    uint32_t hits = 0, pixel = 0, pxy = 0;
+    float ox = 0.f, oy = 0.f, oz = 0.f, dx = 1.f, dy = 1.f, dz = 1.f;
+    uint32_t cur = NONE;                       // item being walked: node index, leaf|slot, or NONE
+    float rMin = 0.f, pMin = 0.f, pMax = 0.f;
+    Hit h; h.t = FLT_MAX; h.slot = -1;
+    bool tracing = false;                      // a ray is in flight (its result has not been recorded)
     uint4 stack[STACK_DEPTH];
     int sp = 0;
-    // pending leaves of the node just visited: A is tested first (near), then B (far)
-    uint32_t leafA = NO_NODE, leafB = NO_NODE;
-    float loA = 0.f, hiA = 0.f, loB = 0.f, hiB = 0.f;
+    uint32_t post = NONE;                      // parked leaf (first slot) when speculating
+    float postLo = 0.f, postHi = 0.f;
+    const uint32_t root_ref = a.hdr->root_axis << BIH_REF_AXIS_SHIFT;
 
-    while (__any_sync(FULL, cur != NO_NODE)) {
-        // ---- phase 1: internal nodes until this lane holds a leaf to test (or runs out of work)
-        while (cur != NO_NODE) {
-            bool advanced = false;
-            if (pMin <= fminf(pMax, h.t)) {                    // entry check (closed interval)
-                const float4 nd = __ldg(reinterpret_cast<const float4*>(nodes + cur));
-                if (COUNTED) nnodes++;
-                const uint32_t rl = __float_as_uint(nd.z), rr = __float_as_uint(nd.w);
-                const uint32_t axis = ((rl >> 30) & 1u) | ((rr >> 29) & 2u);
-                const float org = axis == 0 ? r.ox : (axis == 1 ? r.oy : r.oz);
-                const float inv = axis == 0 ? r.ix : (axis == 1 ? r.iy : r.iz);
-                const bool neg = (r.sign >> axis) & 1u;          // near = sign[axis], :286
-                const float t0 = __fmul_rn(__fsub_rn(nd.x, org), inv);
-                const float t1 = __fmul_rn(__fsub_rn(nd.y, org), inv);
-                const float tn = neg ? t1 : t0, tf = neg ? t0 : t1;
-                const uint32_t refn = neg ? rr : rl, reff = neg ? rl : rr;
-                const bool near_ok = rMin < tn;                  // the reference's strict test, :292
-                const float nMax = fminf(pMax, tn);
-                const float fMin = fmaxf(pMin, tf);
-                const bool near_leaf = (refn & BIH_REF_LEAF) != 0, far_leaf = (reff & BIH_REF_LEAF) != 0;
-                if (near_ok && near_leaf && pMin <= nMax) { leafA = refn & BIH_REF_INDEX; loA = pMin; hiA = nMax; }
-                if (far_leaf && fMin <= pMax) { leafB = reff & BIH_REF_INDEX; loB = fMin; hiB = pMax; }
-                const bool near_i = near_ok && !near_leaf && (pMin <= nMax);
-                const bool far_i = !far_leaf && (fMin <= pMax);
-                if (near_i) {
-                    if (far_i) {
-                        stack[sp] = make_uint4(reff & BIH_REF_INDEX, __float_as_uint(tf), __float_as_uint(fMin), __float_as_uint(pMax));
-                        sp++;
-                        if (COUNTED) maxsp = max(maxsp, (uint32_t)sp);
+    for (;;) {
+        // ================= refill: lanes whose ray has ended record it and get the next one ========
+        const uint32_t idle = __ballot_sync(FULL, cur == NONE && post == NONE);
+        const uint32_t busy = ~idle;
+        if (idle && (busy == 0 || __popc(idle) >= a.refill_threshold)) {
+            bool want_item = false;
+            if (cur == NONE && post == NONE) {
+                if (tracing) {                                   // record the ray that just ended
+                    tracing = false;
+                    if (MODE == 1) hits += (h.slot >= 0);
+                    else {
+                        const uint64_t o = MODE == 0 ? item : (uint64_t)pixel * (uint32_t)nsamp + (uint32_t)s;
+                        if (a.out_t) a.out_t[o] = h.t;
+                        if (a.out_slot) a.out_slot[o] = h.slot;
+                        if (a.out_prim) a.out_prim[o] = h.slot >= 0 ? (int32_t)tris[h.slot].prim : -1;
                     }
-                    cur = refn & BIH_REF_INDEX; pMax = nMax; advanced = true;
-                } else if (far_i) {
-                    cur = reff & BIH_REF_INDEX; rMin = tf; pMin = fMin; advanced = true;
+                    s++;
+                    if (s == nsamp) {
+                        if (MODE == 1) {
+                            // Color + rgbToInt, R/src/CUDAKernels.cu:82-88,385-387,420-422 (sums of 255/20/40 are exact)
+                            const float fh = (float)hits, fm = (float)(nsamp - (int)hits), fs = (float)nsamp;
+                            float cr = __fdiv_rn(__fadd_rn(__fmul_rn(fh, 255.f), __fmul_rn(fm, 20.f)), fs);
+                            float cb = __fdiv_rn(__fmul_rn(fm, 40.f), fs);
+                            cr = fmaxf(0.f, fminf(255.f, cr));
+                            cb = fmaxf(0.f, fminf(255.f, cb));
+                            a.fb[pixel] = ((uint32_t)(int)cb << 16) | ((uint32_t)(int)cr << 8) | (uint32_t)(int)cr;
+                        }
+                        item = ~0ull;
+                    }
+                }
+                want_item = (item == ~0ull);
+            }
+            // hand out new items (warp-uniform control flow)
+            uint32_t want = __ballot_sync(FULL, want_item);
+            while (want && !exhausted) {
+                if (pool_next >= pool_end) {
+                    uint32_t base = 0;
+                    if (lane == 0) base = atomicAdd(a.work, (uint32_t)a.chunk_items);
+                    base = __shfl_sync(FULL, base, 0);
+                    if ((uint64_t)base >= total) { exhausted = true; break; }
+                    pool_next = base;
+                    pool_end = min((uint64_t)base + (uint64_t)a.chunk_items, total);
+                }
+                const uint64_t avail = pool_end - pool_next;
+                const uint32_t rank = __popc(want & lt);
+                const bool served = want_item && (uint64_t)rank < avail;
+                if (served) {
+                    item = pool_next + rank; s = 0; hits = 0; want_item = false;
+                    if (MODE != 0) {
+                        const uint32_t m = (uint32_t)(item >> 10), q = (uint32_t)item & 1023u;
+                        const int tile = a.shard_index + (int)m * a.shard_count;
+                        const int px = (tile % tx) * 32 + (int)((q >> 5) & 3u) * 8 + (int)(q & 7u);
+                        const int py = (tile / tx) * 32 + (int)(q >> 7) * 4 + (int)((q >> 3) & 3u);
+                        if (px < a.w && py < a.h) { pixel = (uint32_t)(py * a.w + px); pxy = (uint32_t)px | ((uint32_t)py << 16); }
+                        else item = ~0ull;                                   // padding pixel of an edge tile
+                        if (item == ~0ull) want_item = true;
+                    }
+                }
+                pool_next += min((uint64_t)__popc(want), avail);
+                // lanes that drew a padding pixel, or were not served, ask again
+                want = __ballot_sync(FULL, want_item);
+            }
+            // start the next ray of every idle lane that owns an item
+            if (cur == NONE && post == NONE && item != ~0ull) {
+                if (MODE == 0) {
+                    const float* p = reinterpret_cast<const float*>(a.rays + item);
+                    ox = __ldg(p); oy = __ldg(p + 1); oz = __ldg(p + 2); dx = __ldg(p + 3); dy = __ldg(p + 4); dz = __ldg(p + 5);
+                } else {
+                    // u,v per R/src/CUDAKernels.cu:414-415; GetRay per R/src/Camera.cu:18-20
+                    const int px = (int)(pxy & 0xFFFFu), py = (int)(pxy >> 16);
+                    const float ru = (a.flags & BIHRT_RENDER_JITTER) ? bihrt_jitter(a.seed, pixel, (uint32_t)s, 0) : 0.5f;
+                    const float rv = (a.flags & BIHRT_RENDER_JITTER) ? bihrt_jitter(a.seed, pixel, (uint32_t)s, 1) : 0.5f;
+                    const float uu = __fdiv_rn(__fadd_rn((float)px, ru), (float)a.w);
+                    const float vv = __fdiv_rn(__fadd_rn((float)py, rv), (float)a.h);
+                    ox = a.cam.origin[0]; oy = a.cam.origin[1]; oz = a.cam.origin[2];
+                    dx = __fsub_rn(__fadd_rn(__fadd_rn(a.cam.lower_left[0], __fmul_rn(uu, a.cam.horizontal[0])), __fmul_rn(vv, a.cam.vertical[0])), ox);
+                    dy = __fsub_rn(__fadd_rn(__fadd_rn(a.cam.lower_left[1], __fmul_rn(uu, a.cam.horizontal[1])), __fmul_rn(vv, a.cam.vertical[1])), oy);
+                    dz = __fsub_rn(__fadd_rn(__fadd_rn(a.cam.lower_left[2], __fmul_rn(uu, a.cam.horizontal[2])), __fmul_rn(vv, a.cam.vertical[2])), oz);
+                }
+                // Ray::Ray, R/src/Ray.cu:3-10
+                const float ix = __frcp_rn(dx), iy = __frcp_rn(dy), iz = __frcp_rn(dz);
+                my_ray[0] = make_float2(ox, ix); my_ray[1] = make_float2(oy, iy); my_ray[2] = make_float2(oz, iz);
+                h.t = FLT_MAX; h.slot = -1; sp = 0; tracing = true;
+                // slab test against the scene box, R/src/CUDAKernels.cu:237-262 (same operation order)
+                bool in = nu > 0;
+                float tMin = __fmul_rn(__fsub_rn(ix < 0.f ? bhi[0] : blo[0], ox), ix);
+                float tMax = __fmul_rn(__fsub_rn(ix < 0.f ? blo[0] : bhi[0], ox), ix);
+                const float tymin = __fmul_rn(__fsub_rn(iy < 0.f ? bhi[1] : blo[1], oy), iy);
+                const float tymax = __fmul_rn(__fsub_rn(iy < 0.f ? blo[1] : bhi[1], oy), iy);
+                if ((tMin > tymax) || (tymin > tMax)) in = false;
+                if (tymin > tMin) tMin = tymin;
+                if (tymax < tMax) tMax = tymax;
+                const float tzmin = __fmul_rn(__fsub_rn(iz < 0.f ? bhi[2] : blo[2], oz), iz);
+                const float tzmax = __fmul_rn(__fsub_rn(iz < 0.f ? blo[2] : bhi[2], oz), iz);
+                if ((tMin > tzmax) || (tzmin > tMax)) in = false;
+                if (tzmin > tMin) tMin = tzmin;
+                if (tzmax < tMax) tMax = tzmax;
+                if (in) {
+                    rMin = tMin; pMin = fmaxf(tMin, 0.f); pMax = tMax;
+                    // Nu == 1: no internal node; the single leaf starts at slot 0 (and must not be
+                    // interval-pruned: the reference tests it unconditionally once the box is hit)
+                    if (nu == 1) { cur = BIH_REF_LEAF; pMin = -FLT_MAX; pMax = FLT_MAX; }
+                    else cur = root_ref;
                 }
             }
-            if (!advanced) {
+            if (__ballot_sync(FULL, cur != NONE || post != NONE || tracing) == 0 && exhausted &&
+                __ballot_sync(FULL, item != ~0ull) == 0) break;
+        }
+
+        // ================= phase 1: internal nodes =====================================================
+        // A lane steps through nodes until it holds a leaf.  With `speculate` it parks that leaf (one
+        // slot) and keeps walking -- leaves are still tested in traversal order and re-checked against
+        // the closest hit when their turn comes, so results are unchanged; only some node visits are
+        // wasted.  The warp leaves the phase when nobody has a node left, or -- `vote` -- as soon as
+        // the lanes holding a leaf outnumber (vote 2) / reach `leaf_votes` (vote 1) the lanes walking.
+        for (;;) {
+            if ((int)cur >= 0) {
+                bool popit = true;
+                if (pMin <= fminf(pMax, h.t)) {                        // entry check (closed interval)
+                    const float2 oi = my_ray[cur >> BIH_REF_AXIS_SHIFT];   // (origin, 1/dir) on this node's axis
+                    const float4 nd = __ldg(reinterpret_cast<const float4*>(nodes + (cur & BIH_REF_INDEX)));
+                    if (COUNTED) nnodes++;
+                    const uint32_t rl = __float_as_uint(nd.z), rr = __float_as_uint(nd.w);
+                    const bool neg = oi.y < 0.f;                           // near = sign[axis], :286
+                    const float t0 = __fmul_rn(__fsub_rn(nd.x, oi.x), oi.y);   // :288-289
+                    const float t1 = __fmul_rn(__fsub_rn(nd.y, oi.x), oi.y);
+                    const float tn = neg ? t1 : t0, tf = neg ? t0 : t1;
+                    const uint32_t refn = neg ? rr : rl, reff = neg ? rl : rr;
+                    const float nMax = fminf(pMax, tn);
+                    const float fMin = fmaxf(pMin, tf);
+                    const bool go_near = (rMin < tn) && (pMin <= nMax);   // reference's strict test (:292) + closed tight interval
+                    const bool go_far = (fMin <= pMax);
+                    if (go_near && go_far) {
+                        // near before far, except a far LEAF next to a near NODE is tested first (:344-349)
+                        if ((int)refn >= 0 && (int)reff < 0) {
+                            stack[sp] = make_uint4(refn, __float_as_uint(rMin), __float_as_uint(pMin), __float_as_uint(nMax));
+                            cur = reff; rMin = tf; pMin = fMin;
+                        } else {
+                            stack[sp] = make_uint4(reff, __float_as_uint(tf), __float_as_uint(fMin), __float_as_uint(pMax));
+                            cur = refn; pMax = nMax;
+                        }
+                        sp++;
+                        if (COUNTED) maxsp = max(maxsp, (uint32_t)sp);
+                        popit = false;
+                    } else if (go_near) { cur = refn; pMax = nMax; popit = false; }
+                    else if (go_far) { cur = reff; rMin = tf; pMin = fMin; popit = false; }
+                }
+                if (popit) {
+                    if (sp > 0) {
+                        sp--;
+                        const uint4 e = stack[sp];
+                        cur = e.x; rMin = __uint_as_float(e.y); pMin = __uint_as_float(e.z); pMax = __uint_as_float(e.w);
+                    } else cur = NONE;
+                }
+            } else if (a.speculate && cur != NONE && post == NONE) {
+                // park the leaf, continue with the next item
+                post = cur & BIH_REF_INDEX; postLo = pMin; postHi = pMax;
                 if (sp > 0) {
                     sp--;
                     const uint4 e = stack[sp];
                     cur = e.x; rMin = __uint_as_float(e.y); pMin = __uint_as_float(e.z); pMax = __uint_as_float(e.w);
-                } else cur = NO_NODE;
+                } else cur = NONE;
             }
-            if ((leafA & leafB) != NO_NODE) break;               // something to test
+            const uint32_t m_node = __ballot_sync(FULL, (int)cur >= 0);
+            if (m_node == 0) break;
+            if (a.vote) {
+                const uint32_t m_wait = __ballot_sync(FULL, (int)cur < 0 && (cur != NONE || post != NONE) && !(a.speculate && post == NONE));
+                if (a.vote == 1 ? (__popc(m_wait) >= a.leaf_votes)
+                    : a.vote == 2 ? (__popc(m_wait) > __popc(m_node))
+                                  : (m_wait != 0 && __popc(m_node) <= a.leaf_votes)) break;
+            }
+        }
+        // ================= phase 2: the leaves this lane holds, in traversal order =====================
+        if (post != NONE) {
+            if (postLo <= fminf(postHi, h.t)) test_leaf<COUNTED>(tris, post, ox, oy, oz, dx, dy, dz, h, ntris);
+            post = NONE;
+        }
+        if ((int)cur < 0 && cur != NONE) {
+            if (pMin <= fminf(pMax, h.t)) test_leaf<COUNTED>(tris, cur & BIH_REF_INDEX, ox, oy, oz, dx, dy, dz, h, ntris);
+            if (sp > 0) {
+                sp--;
+                const uint4 e = stack[sp];
+                cur = e.x; rMin = __uint_as_float(e.y); pMin = __uint_as_float(e.z); pMax = __uint_as_float(e.w);
+            } else cur = NONE;
         }
         __syncwarp();
-        // ---- phase 2: leaves, near first; each is re-checked against the closest hit so far
-        if (leafA != NO_NODE) {
-            if (loA <= fminf(hiA, h.t)) test_leaf<COUNTED>(tris, leafA, r, h, ntris);
-            leafA = NO_NODE;
-        }
-        if (leafB != NO_NODE) {
-            if (loB <= fminf(hiB, h.t)) test_leaf<COUNTED>(tris, leafB, r, h, ntris);
-            leafB = NO_NODE;
-        }
-        __syncwarp();
     }
-}
 
-// ------------------------------------------------------------------------------------------
-// kernels.  MODE 0: ray list -> (t, slot, prim);  1: camera -> packed framebuffer;
-//           2: camera -> per-sample (t, slot, prim)
-// ------------------------------------------------------------------------------------------
-template <int MODE, bool COUNTED>
-__global__ void __launch_bounds__(128) k_trace(TraceArgs a) {
-    const int lane = threadIdx.x & 31;
-    const BihHeader* hdr = a.hdr;
-    const uint32_t nu = hdr->nu;
-    float lo[3] = { hdr->lo[0], hdr->lo[1], hdr->lo[2] }, hi[3] = { hdr->hi[0], hdr->hi[1], hdr->hi[2] };
-    uint32_t nnodes = 0, ntris = 0, maxsp = 0;
-
-    // work units
-    uint32_t nunits;
-    int tx = 0, my_tiles = 0;
-    if (MODE == 0) nunits = (uint32_t)((a.nrays + 31) / 32);
-    else {
-        tx = (a.w + 31) / 32;
-        const int ty = (a.h + 31) / 32, T = tx * ty;
-        my_tiles = T > a.shard_index ? (T - a.shard_index + a.shard_count - 1) / a.shard_count : 0;
-        nunits = (uint32_t)my_tiles * 32u;
-    }
-    for (;;) {
-        uint32_t u = 0;
-        if (lane == 0) u = atomicAdd(a.work, 1u);
-        u = __shfl_sync(FULL, u, 0);
-        if (u >= nunits) break;
-        if (MODE == 0) {
-            const int64_t i = (int64_t)u * 32 + lane;
-            const bool active = i < a.nrays;
-            Ray r = make_ray(0.f, 0.f, 0.f, 1.f, 1.f, 1.f);
-            if (active) {
-                const float* p = reinterpret_cast<const float*>(a.rays + i);
-                r = make_ray(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3), __ldg(p + 4), __ldg(p + 5));
-            }
-            Hit h;
-            trace_ray<COUNTED>(a.nodes, a.tris, nu, lo, hi, active, r, h, nnodes, ntris, maxsp);
-            if (active) {
-                if (a.out_t) a.out_t[i] = h.t;
-                if (a.out_slot) a.out_slot[i] = h.slot;
-                if (a.out_prim) a.out_prim[i] = (int32_t)h.prim;
-            }
-        } else {
-            const int tile = a.shard_index + (int)(u >> 5) * a.shard_count;
-            const int sub = (int)(u & 31u);
-            const int px = (tile % tx) * 32 + (sub & 3) * 8 + (lane & 7);
-            const int py = (tile / tx) * 32 + (sub >> 2) * 4 + (lane >> 3);
-            const bool inside = px < a.w && py < a.h;
-            const uint32_t pixel = (uint32_t)(py * a.w + px);
-            uint32_t hits = 0;
-            for (int s = 0; s < a.spp; s++) {
-                // u,v per R/src/CUDAKernels.cu:414-415; GetRay per R/src/Camera.cu:18-20
-                const float ru = (a.flags & BIHRT_RENDER_JITTER) ? bihrt_jitter(a.seed, pixel, (uint32_t)s, 0) : 0.5f;
-                const float rv = (a.flags & BIHRT_RENDER_JITTER) ? bihrt_jitter(a.seed, pixel, (uint32_t)s, 1) : 0.5f;
-                const float uu = __fdiv_rn(__fadd_rn((float)px, ru), (float)a.w);
-                const float vv = __fdiv_rn(__fadd_rn((float)py, rv), (float)a.h);
-                float d[3];
-#pragma unroll
-                for (int k = 0; k < 3; k++)
-                    d[k] = __fsub_rn(__fadd_rn(__fadd_rn(a.cam.lower_left[k], __fmul_rn(uu, a.cam.horizontal[k])),
-                                               __fmul_rn(vv, a.cam.vertical[k])), a.cam.origin[k]);
-                const Ray r = make_ray(a.cam.origin[0], a.cam.origin[1], a.cam.origin[2], d[0], d[1], d[2]);
-                Hit h;
-                trace_ray<COUNTED>(a.nodes, a.tris, nu, lo, hi, inside, r, h, nnodes, ntris, maxsp);
-                if (MODE == 1) hits += (h.slot >= 0);
-                else if (inside) {
-                    const int64_t o = (int64_t)pixel * a.spp + s;
-                    if (a.out_t) a.out_t[o] = h.t;
-                    if (a.out_slot) a.out_slot[o] = h.slot;
-                    if (a.out_prim) a.out_prim[o] = (int32_t)h.prim;
-                }
-            }
-            if (MODE == 1 && inside) {
-                // Color + rgbToInt, R/src/CUDAKernels.cu:82-88,385-387,420-422 (sums of 255/20/40 are exact)
-                const float fh = (float)hits, fm = (float)(a.spp - (int)hits), fs = (float)a.spp;
-                float cr = __fdiv_rn(__fadd_rn(__fmul_rn(fh, 255.f), __fmul_rn(fm, 20.f)), fs);
-                float cb = __fdiv_rn(__fmul_rn(fm, 40.f), fs);
-                cr = fmaxf(0.f, fminf(255.f, cr));
-                cb = fmaxf(0.f, fminf(255.f, cb));
-                a.fb[pixel] = ((uint32_t)(int)cb << 16) | ((uint32_t)(int)cr << 8) | (uint32_t)(int)cr;
-            }
-        }
-    }
     if (COUNTED) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -271,11 +320,11 @@ template <int MODE, bool COUNTED>
 static int launch(bihrt_ctx* c, const TraceArgs& a) {
     int per_sm = c->opt_trace_blocks_per_sm;
     if (per_sm <= 0) {
-        BIHRT_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<MODE, COUNTED>, 128, 0));
+        BIHRT_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<MODE, COUNTED>, TRACE_THREADS, 0));
         if (per_sm < 1) per_sm = 1;
     }
     BIHRT_CUDA(c, cudaMemsetAsync(a.work, 0, 4, c->stream));
-    k_trace<MODE, COUNTED><<<c->sm_count * per_sm, 128, 0, c->stream>>>(a);
+    k_trace<MODE, COUNTED><<<c->sm_count * per_sm, TRACE_THREADS, 0, c->stream>>>(a);
     c->kernel_launches += 1;
     BIHRT_CUDA(c, cudaGetLastError());
     return BIHRT_OK;

@@ -440,8 +440,9 @@ static void traverse_ref(const orc_scene* s, const orc_ray* r, orc_hit* rec, orc
  *   far child considered  <=> the CLOSED tight interval [max(pMin, t[far]), pMax] is non-empty
  *                             (this implies the reference's !(tMax < t[far]), :293, because the
  *                             reference's tMax is never below pMax);
- *   a considered child (leaf or node) is actually entered only if its tight interval, cut at the
- *   closest hit found so far, is still non-empty at the moment it is entered.
+ *   a considered child (leaf or node) becomes an item (reference + bounds) and is actually entered
+ *   only if its tight interval, cut at the closest hit found so far, is still non-empty when its
+ *   turn comes.
  * So the visited leaves are a subset of the reference's, and a leaf is only dropped when its
  * tight interval is empty or starts beyond the closest hit: the result equals TraverseTree's
  * except when Moller-Trumbore's rounded t disagrees with the rounded plane distances at an
@@ -456,40 +457,52 @@ static void traverse_proper(const orc_scene* s, const orc_ray* r, orc_hit* rec, 
     if (!scene_slab(s, r, &rMin, &sMax)) return;
     if (s->nu == 1) { find_nearest(s, r, 0, rec, c); return; }
     float pMin = dev_fmaxf(rMin, 0.0f), pMax = sMax;
-    struct { int node; float rMin, pMin, pMax; } stack[64];
+    /* item = child reference (>= 0: internal node, < 0: leaf ~ref) + its three interval bounds;
+     * a leaf is an item like a node, so the traversal has one stack and one entry check */
+    struct { int ref; float rMin, pMin, pMax; } stack[64];
     int sp = 0;
     int cur = 0;
     for (;;) {
-        /* entry check: tight interval, shrunk to the closest hit so far, must be non-empty (closed) */
+        int next = 0;
+        /* entry check: tight interval, cut at the closest hit so far, must be non-empty (closed) */
         if (pMin <= dev_fminf(pMax, (float)rec->t)) {
-            c->nodes++;
-            int ax = s->axis[cur];
-            float org = r->o[ax], inv = r->inv[ax];
-            int near = r->sign[ax], far = 1 - near;
-            float t0 = (s->clip[2 * cur] - org) * inv;
-            float t1 = (s->clip[2 * cur + 1] - org) * inv;
-            float tn = near ? t1 : t0, tf = near ? t0 : t1;
-            const uint8_t* lf = s->is_leaf + 2 * cur;
-            const int32_t* ch = s->children + 2 * cur;
-            int near_ok = (rMin < tn);                              /* the reference's strict test, :292 */
-            float nMax = dev_fminf(pMax, tn);                       /* near: [pMin, nMax] */
-            float fMin = dev_fmaxf(pMin, tf);                       /* far : [fMin, pMax] */
-            /* leaf children are tested here, near first (reference order :337-338,346,352) */
-            if (near_ok && lf[near] && pMin <= dev_fminf(nMax, (float)rec->t)) find_nearest(s, r, ch[near], rec, c);
-            if (lf[far] && fMin <= dev_fminf(pMax, (float)rec->t)) find_nearest(s, r, ch[far], rec, c);
-            int near_i = near_ok && !lf[near] && (pMin <= nMax);
-            int far_i = !lf[far] && (fMin <= pMax);
-            if (near_i && far_i) {
-                stack[sp].node = ch[far]; stack[sp].rMin = tf; stack[sp].pMin = fMin; stack[sp].pMax = pMax; sp++;
-                if (sp > c->max_stack) c->max_stack = sp;
-                cur = ch[near]; pMax = nMax;
-                continue;
-            } else if (near_i) { cur = ch[near]; pMax = nMax; continue; }
-            else if (far_i) { cur = ch[far]; rMin = tf; pMin = fMin; continue; }
+            if (cur < 0) {
+                find_nearest(s, r, ~cur, rec, c);
+            } else {
+                c->nodes++;
+                int ax = s->axis[cur];
+                float org = r->o[ax], inv = r->inv[ax];
+                int near = r->sign[ax], far = 1 - near;
+                float t0 = (s->clip[2 * cur] - org) * inv;
+                float t1 = (s->clip[2 * cur + 1] - org) * inv;
+                float tn = near ? t1 : t0, tf = near ? t0 : t1;
+                const uint8_t* lf = s->is_leaf + 2 * cur;
+                const int32_t* ch = s->children + 2 * cur;
+                int refn = lf[near] ? ~ch[near] : ch[near], reff = lf[far] ? ~ch[far] : ch[far];
+                float nMax = dev_fminf(pMax, tn);                   /* near: [pMin, nMax] */
+                float fMin = dev_fmaxf(pMin, tf);                   /* far : [fMin, pMax] */
+                int go_near = (rMin < tn) && (pMin <= nMax);        /* reference's strict test (:292) + closed tight interval */
+                int go_far = (fMin <= pMax);
+                if (go_near && go_far) {
+                    /* near before far, except a far LEAF next to a near NODE is tested first (:344-349) */
+                    if (refn >= 0 && reff < 0) {
+                        stack[sp].ref = refn; stack[sp].rMin = rMin; stack[sp].pMin = pMin; stack[sp].pMax = nMax;
+                        cur = reff; rMin = tf; pMin = fMin;
+                    } else {
+                        stack[sp].ref = reff; stack[sp].rMin = tf; stack[sp].pMin = fMin; stack[sp].pMax = pMax;
+                        cur = refn; pMax = nMax;
+                    }
+                    sp++;
+                    if (sp > c->max_stack) c->max_stack = sp;
+                    next = 1;
+                } else if (go_near) { cur = refn; pMax = nMax; next = 1; }
+                else if (go_far) { cur = reff; rMin = tf; pMin = fMin; next = 1; }
+            }
         }
+        if (next) continue;
         if (sp == 0) break;
         sp--;
-        cur = stack[sp].node; rMin = stack[sp].rMin; pMin = stack[sp].pMin; pMax = stack[sp].pMax;
+        cur = stack[sp].ref; rMin = stack[sp].rMin; pMin = stack[sp].pMin; pMax = stack[sp].pMax;
     }
 }
 
