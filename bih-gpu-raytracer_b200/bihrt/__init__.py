@@ -76,7 +76,7 @@ def load_library(path=None):
     """dlopen libbihrt.so (no CUDA call is made).  Raises if the library has not been built."""
     global _lib
     if _lib is None or path:
-        p = path or LIB_PATH
+        p = path or os.environ.get("BIHRT_LIB") or LIB_PATH
         if not os.path.exists(p):
             raise BihrtError(-100, "%s not found: build it with `make -C %s` (there is no CPU fallback)" % (p, _PKG))
         lib = C.CDLL(p)

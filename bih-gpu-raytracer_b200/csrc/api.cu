@@ -156,9 +156,8 @@ int bihrt_set_option(bihrt_ctx* c, const char* name, int64_t v) {
     if (!strcmp(name, "trace_blocks_per_sm")) c->opt_trace_blocks_per_sm = (int)v;
     else if (!strcmp(name, "trace_variant")) c->opt_trace_variant = (int)v;
     else if (!strcmp(name, "trace_refill_threshold")) c->opt_refill_threshold = (int)std::max<int64_t>(1, std::min<int64_t>(32, v));
-    else if (!strcmp(name, "trace_vote")) c->opt_vote = (int)v;
-    else if (!strcmp(name, "trace_leaf_votes")) c->opt_leaf_votes = (int)v;
-    else if (!strcmp(name, "trace_speculate")) c->opt_speculate = (int)v;
+    else if (!strcmp(name, "trace_vote_wait")) c->opt_vote_wait = (int)v;
+    else if (!strcmp(name, "trace_vote_walk")) c->opt_vote_walk = (int)v;
     else if (!strcmp(name, "trace_chunk_items")) c->opt_chunk_items = (int)std::max<int64_t>(32, (v + 31) / 32 * 32);
     else return bihrt_fail(c, BIHRT_ERR_INVALID, "unknown option '%s'", name);
     return BIHRT_OK;
@@ -311,15 +310,15 @@ int bihrt_export_reference_view(bihrt_ctx* c, bihrt_refview* v) {
     for (size_t i = 0; i < ni; i++) {
         const BihNode& nd = nodes[i];
         const bool ll = nd.ref_l & BIH_REF_LEAF, rl = nd.ref_r & BIH_REF_LEAF;
-        const uint32_t il = nd.ref_l & BIH_REF_INDEX, ir = nd.ref_r & BIH_REF_INDEX;
+        const uint32_t il = BIH_REF_INDEX(nd.ref_l), ir = BIH_REF_INDEX(nd.ref_r);
         uint32_t split;
         if (!ll) split = il;
         else if (!rl) split = ir - 1;
         else split = (uint32_t)(std::lower_bound(first.begin(), first.begin() + nu, il) - first.begin());   // leaf whose first slot is il
         if (v->clip_planes) { v->clip_planes[2 * i] = nd.clip0; v->clip_planes[2 * i + 1] = nd.clip1; }
         if (v->axis) {      // a node's axis is stored in its parent's reference to it
-            if (!ll) v->axis[split] = (int32_t)((nd.ref_l >> BIH_REF_AXIS_SHIFT) & 3u);
-            if (!rl) v->axis[split + 1] = (int32_t)((nd.ref_r >> BIH_REF_AXIS_SHIFT) & 3u);
+            if (!ll) v->axis[split] = (int32_t)BIH_REF_AXIS(nd.ref_l);
+            if (!rl) v->axis[split + 1] = (int32_t)BIH_REF_AXIS(nd.ref_r);
         }
         if (v->is_leaf) { v->is_leaf[2 * i] = ll; v->is_leaf[2 * i + 1] = rl; }
         if (v->children) { v->children[2 * i] = (int32_t)split; v->children[2 * i + 1] = (int32_t)split + 1; }
@@ -345,7 +344,7 @@ static void base_args(bihrt_ctx* c, TraceArgs& a) {
     a.counters = c->d_counters; a.work = c->d_work;
     a.shard_index = 0; a.shard_count = 1;
     a.refill_threshold = c->opt_refill_threshold; a.chunk_items = c->opt_chunk_items;
-    a.vote = c->opt_vote; a.leaf_votes = c->opt_leaf_votes; a.speculate = c->opt_speculate;
+    a.vote_wait = c->opt_vote_wait; a.vote_walk = c->opt_vote_walk;
 }
 
 // outputs may individually be host or device; host ones are staged through d_io

@@ -11,10 +11,11 @@
 // Node, 16 B, one LDG.128 per visit.  Index = the reference's (Karras) node index, so node i here is
 // TreeInternalNode i of R/src/Tree.cuh:16-24.  A child reference packs
 //   bit 31     : child is a leaf
-//   bits 30..29: split axis OF THE CHILD (internal children; 0 for leaves) -- the traversal knows the
+//   bits 30..2 : internal child -> node index; leaf child -> first slot of the leaf in tris[]
+//                (so (ref & ~3) * 4 is the node's byte offset and (ref & 0x7FFFFFFC) * 12 the triangle's)
+//   bits 1..0  : split axis OF THE CHILD (internal children; 0 for leaves) -- the traversal knows the
 //                axis of a node before it fetches it, so the ray constants for that axis are loaded
 //                in parallel with the node instead of after it.  The root's axis is in the header.
-//   bits 28..0 : internal child -> node index; leaf child -> first slot of the leaf in tris[]
 struct __align__(16) BihNode {
     float    clip0;   // max over the left subtree of hi[axis]   (t_clipPlanes[0])
     float    clip1;   // min over the right subtree of lo[axis]  (t_clipPlanes[1])
@@ -22,13 +23,15 @@ struct __align__(16) BihNode {
     uint32_t ref_r;
 };
 #define BIH_REF_LEAF  0x80000000u
-#define BIH_REF_AXIS_SHIFT 29
-#define BIH_REF_INDEX 0x1FFFFFFFu
+#define BIH_REF_NODE(idx, axis) (((uint32_t)(idx) << 2) | (uint32_t)(axis))
+#define BIH_REF_LEAFREF(slot)   (BIH_REF_LEAF | ((uint32_t)(slot) << 2))
+#define BIH_REF_INDEX(ref)      (((ref) & 0x7FFFFFFFu) >> 2)
+#define BIH_REF_AXIS(ref)       ((ref) & 3u)
 #define BIH_MAX_TRIS  (1ll << 29)
 
 // Leaf-ordered triangle, 48 B = 3 x LDG.128: v0, e1 = v1 - v0, e2 = v2 - v0 (the two edges
 // RayTriangleIntersection recomputes per test, R/src/CUDAKernels.cu:18-19), the input triangle index
-// (m_trisIndexes[slot]) and an end-of-leaf flag.  Slot order = Morton-sorted order, so a leaf is a
+// (m_trisIndexes[slot]), an end-of-leaf flag and the slot number itself.  Slot order = Morton-sorted order, so a leaf is a
 // contiguous run and the reference's triangleIdxs[] / firstIdxs[] / duplicatesCnts[] indirections
 // (R/src/CUDAKernels.cu:215-217) are gone from the traversal.
 struct __align__(16) BihTri {
@@ -37,7 +40,7 @@ struct __align__(16) BihTri {
     float    e2z;
     uint32_t prim;
     uint32_t last;     // 1 on the last triangle of its leaf
-    uint32_t pad;
+    uint32_t slot;     // this record's own index (= the reference's HitRecord::triangleIdx)
 };
 
 struct SceneBox { float lo[3]; float hi[3]; };
@@ -102,7 +105,7 @@ struct bihrt_ctx {
     int opt_trace_variant = 0;
     int opt_refill_threshold = 32;
     int opt_chunk_items = 32;
-    int opt_vote = 0, opt_leaf_votes = 16, opt_speculate = 0;
+    int opt_vote_wait = 1, opt_vote_walk = 1;
     int opt_sort_passes = 4;
     int64_t kernel_launches = 0;
 };
@@ -124,9 +127,7 @@ struct TraceArgs {
     unsigned long long* counters; uint32_t* work;
     int refill_threshold;   // lanes whose ray ended wait until this many are idle (or nobody is busy)
     int chunk_items;        // work items (rays / pixels) a warp takes from the global counter at once
-    int vote;               // 0: node phase ends when no lane has a node; 1: ... or leaf_votes lanes wait; 2: ... or waiters > walkers
-    int leaf_votes;
-    int speculate;          // park one leaf and keep walking
+    int vote_wait, vote_walk;   // node phase also ends when waiters * vote_wait > walkers * vote_walk (0,x = never)
 };
 int bihrt_trace_launch(bihrt_ctx* c, const TraceArgs& a, int mode /*0 rays,1 render fb,2 render hits*/, bool counted);
 

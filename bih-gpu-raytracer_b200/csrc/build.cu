@@ -398,7 +398,7 @@ __global__ void __launch_bounds__(128) k_tree(const float* __restrict__ tri_in, 
         }
         float4 q0 = make_float4(v[0], v[1], v[2], __fsub_rn(v[3], v[0]));
         float4 q1 = make_float4(__fsub_rn(v[4], v[1]), __fsub_rn(v[5], v[2]), __fsub_rn(v[6], v[0]), __fsub_rn(v[7], v[1]));
-        float4 q2 = make_float4(__fsub_rn(v[8], v[2]), __uint_as_float(p), __uint_as_float(j + 1 == s1 ? 1u : 0u), 0.0f);
+        float4 q2 = make_float4(__fsub_rn(v[8], v[2]), __uint_as_float(p), __uint_as_float(j + 1 == s1 ? 1u : 0u), __uint_as_float(j));
         float4* dst = reinterpret_cast<float4*>(tris + j);
         dst[0] = q0; dst[1] = q1; dst[2] = q2;
     }
@@ -446,10 +446,8 @@ __global__ void __launch_bounds__(128) k_tree(const float* __restrict__ tri_in, 
         cl1 = pick(rbox.lo, axis);
         // a radix-tree node over leaves [l,r] splits on the first bit in which umc[l] and umc[r] differ,
         // so a child's axis follows from its range ends (== (lcp(children of the child) + 1) % 3)
-        ref_l = (a == ps) ? (BIH_REF_LEAF | first[ps])
-                          : (ps | ((uint32_t)((__clz(umc[a] ^ umc[ps]) + 1) % 3) << BIH_REF_AXIS_SHIFT));
-        ref_r = (ps + 1 == b) ? (BIH_REF_LEAF | first[ps + 1])
-                              : ((ps + 1) | ((uint32_t)((__clz(umc[ps + 1] ^ umc[b]) + 1) % 3) << BIH_REF_AXIS_SHIFT));
+        ref_l = (a == ps) ? BIH_REF_LEAFREF(first[ps]) : BIH_REF_NODE(ps, (__clz(umc[a] ^ umc[ps]) + 1) % 3);
+        ref_r = (ps + 1 == b) ? BIH_REF_LEAFREF(first[ps + 1]) : BIH_REF_NODE(ps + 1, (__clz(umc[ps + 1] ^ umc[b]) + 1) % 3);
         if (a == 0 && b == nu - 1) hdr->root_axis = (uint32_t)axis;
         Box u;
 #pragma unroll

@@ -14,7 +14,7 @@
 //     node's axis bits by one 64-bit LDS instead of a select chain;
 //   * two-phase ("while-while") loop: lanes step through internal nodes until they hold a leaf, the
 //     warp re-converges, leaves are tested, repeat; a vote ends the node phase early when most lanes
-//     already wait with a leaf, and a lane may park one leaf and keep walking (speculation).
+//     already wait with a leaf.
 //
 // Logical per-ray algorithm = oracle/bih_oracle.c:traverse_proper (pruned traversal that returns what
 // the reference's TraverseTree returns, including on axis-aligned flat geometry where the reference's
@@ -27,6 +27,9 @@
 #define STACK_DEPTH 32          // <= 31 items: one per Morton bit on a root-to-leaf path, plus one
 #define NONE 0xFFFFFFFFu        // "no item": leaf bit set, never a valid slot
 #define TRACE_THREADS 128
+#ifndef TRACE_MIN_BLOCKS
+#define TRACE_MIN_BLOCKS 8        // <= 64 registers per thread
+#endif
 
 // (double)det < 0.000001 (R/src/CUDAKernels.cu:28)  <=>  det < 0x358637be as binary32
 #define DET_EPS __uint_as_float(0x358637beu)
@@ -34,10 +37,10 @@
 struct Hit { float t; int slot; };
 
 template <bool COUNTED>
-__device__ __forceinline__ void test_leaf(const BihTri* __restrict__ tris, uint32_t slot, float ox, float oy, float oz,
+__device__ __forceinline__ void test_leaf(const char* __restrict__ first_tri, float ox, float oy, float oz,
                                           float dx, float dy, float dz, Hit& h, uint32_t& ntris) {
+    const float4* p = reinterpret_cast<const float4*>(first_tri);
     for (;;) {
-        const float4* p = reinterpret_cast<const float4*>(tris + slot);
         const float4 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2);
         if (COUNTED) ntris++;
         const float e1x = q0.w, e1y = q1.x, e1z = q1.y, e2x = q1.z, e2y = q1.w, e2z = q2.x;
@@ -57,12 +60,12 @@ __device__ __forceinline__ void test_leaf(const BihTri* __restrict__ tris, uint3
                 const float v = __fmul_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, qx), __fmul_rn(dy, qy)), __fmul_rn(dz, qz)), inv);
                 if (!(v < 0.f || __fadd_rn(u, v) > 1.f)) {
                     const float t = __fmul_rn(__fadd_rn(__fadd_rn(__fmul_rn(e2x, qx), __fmul_rn(e2y, qy)), __fmul_rn(e2z, qz)), inv);
-                    if (t > 0.f && t < h.t) { h.t = t; h.slot = (int)slot; }      // :218-221, slot = sorted index
+                    if (t > 0.f && t < h.t) { h.t = t; h.slot = (int)__float_as_uint(q2.w); }   // :218-221, slot = sorted index
                 }
             }
         }
         if (__float_as_uint(q2.z) & 1u) break;      // last triangle of the leaf
-        slot++;
+        p += 3;
     }
 }
 
@@ -71,14 +74,15 @@ __device__ __forceinline__ void test_leaf(const BihTri* __restrict__ tris, uint3
 // Work item = one ray (MODE 0) or one pixel with its spp samples (MODE 1/2).
 // ------------------------------------------------------------------------------------------
 template <int MODE, bool COUNTED>
-__global__ void __launch_bounds__(TRACE_THREADS) k_trace(TraceArgs a) {
+__global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(TraceArgs a) {
     // per-axis ray constants (origin, 1/dir), one row of 3 float2 per thread: 24-byte stride keeps a
     // half-warp's 64-bit accesses on distinct banks when the lanes agree on the axis
     __shared__ float2 s_ray[TRACE_THREADS * 3];
     const int lane = threadIdx.x & 31;
     const uint32_t lt = (1u << lane) - 1u;
     float2* my_ray = s_ray + threadIdx.x * 3;
-    const BihNode* __restrict__ nodes = a.nodes;
+    const char* __restrict__ nodes_b = reinterpret_cast<const char*>(a.nodes);
+    const char* __restrict__ tris_b = reinterpret_cast<const char*>(a.tris);
     const BihTri* __restrict__ tris = a.tris;
     const uint32_t nu = a.hdr->nu;
     const float blo[3] = { a.hdr->lo[0], a.hdr->lo[1], a.hdr->lo[2] }, bhi[3] = { a.hdr->hi[0], a.hdr->hi[1], a.hdr->hi[2] };
@@ -109,17 +113,16 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace(TraceArgs a) {
     bool tracing = false;                      // a ray is in flight (its result has not been recorded)
     uint4 stack[STACK_DEPTH];
     int sp = 0;
-    uint32_t post = NONE;                      // parked leaf (first slot) when speculating
-    float postLo = 0.f, postHi = 0.f;
-    const uint32_t root_ref = a.hdr->root_axis << BIH_REF_AXIS_SHIFT;
+    const uint32_t root_ref = BIH_REF_NODE(0, a.hdr->root_axis);
+    const int vote_wait = a.vote_wait, vote_walk = a.vote_walk;
 
     for (;;) {
         // ================= refill: lanes whose ray has ended record it and get the next one ========
-        const uint32_t idle = __ballot_sync(FULL, cur == NONE && post == NONE);
+        const uint32_t idle = __ballot_sync(FULL, cur == NONE);
         const uint32_t busy = ~idle;
         if (idle && (busy == 0 || __popc(idle) >= a.refill_threshold)) {
             bool want_item = false;
-            if (cur == NONE && post == NONE) {
+            if (cur == NONE) {
                 if (tracing) {                                   // record the ray that just ended
                     tracing = false;
                     if (MODE == 1) hits += (h.slot >= 0);
@@ -176,7 +179,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace(TraceArgs a) {
                 want = __ballot_sync(FULL, want_item);
             }
             // start the next ray of every idle lane that owns an item
-            if (cur == NONE && post == NONE && item != ~0ull) {
+            if (cur == NONE && item != ~0ull) {
                 if (MODE == 0) {
                     const float* p = reinterpret_cast<const float*>(a.rays + item);
                     ox = __ldg(p); oy = __ldg(p + 1); oz = __ldg(p + 2); dx = __ldg(p + 3); dy = __ldg(p + 4); dz = __ldg(p + 5);
@@ -214,26 +217,25 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace(TraceArgs a) {
                     rMin = tMin; pMin = fmaxf(tMin, 0.f); pMax = tMax;
                     // Nu == 1: no internal node; the single leaf starts at slot 0 (and must not be
                     // interval-pruned: the reference tests it unconditionally once the box is hit)
-                    if (nu == 1) { cur = BIH_REF_LEAF; pMin = -FLT_MAX; pMax = FLT_MAX; }
+                    if (nu == 1) { cur = BIH_REF_LEAFREF(0); pMin = -FLT_MAX; pMax = FLT_MAX; }
                     else cur = root_ref;
                 }
             }
-            if (__ballot_sync(FULL, cur != NONE || post != NONE || tracing) == 0 && exhausted &&
+            if (__ballot_sync(FULL, cur != NONE || tracing) == 0 && exhausted &&
                 __ballot_sync(FULL, item != ~0ull) == 0) break;
         }
 
         // ================= phase 1: internal nodes =====================================================
-        // A lane steps through nodes until it holds a leaf.  With `speculate` it parks that leaf (one
-        // slot) and keeps walking -- leaves are still tested in traversal order and re-checked against
-        // the closest hit when their turn comes, so results are unchanged; only some node visits are
-        // wasted.  The warp leaves the phase when nobody has a node left, or -- `vote` -- as soon as
-        // the lanes holding a leaf outnumber (vote 2) / reach `leaf_votes` (vote 1) the lanes walking.
+        // A lane steps through nodes until it holds a leaf, then waits.  The warp leaves the phase when
+        // nobody has a node left, or as soon as the waiting lanes outweigh the walking ones
+        // (waiters * vote_wait > walkers * vote_walk): finishing the node phase for a few stragglers
+        // with most lanes idle costs more than testing the held leaves first.
         for (;;) {
             if ((int)cur >= 0) {
                 bool popit = true;
                 if (pMin <= fminf(pMax, h.t)) {                        // entry check (closed interval)
-                    const float2 oi = my_ray[cur >> BIH_REF_AXIS_SHIFT];   // (origin, 1/dir) on this node's axis
-                    const float4 nd = __ldg(reinterpret_cast<const float4*>(nodes + (cur & BIH_REF_INDEX)));
+                    const float2 oi = my_ray[BIH_REF_AXIS(cur)];           // (origin, 1/dir) on this node's axis
+                    const float4 nd = __ldg(reinterpret_cast<const float4*>(nodes_b + (size_t)(cur & ~3u) * 4));
                     if (COUNTED) nnodes++;
                     const uint32_t rl = __float_as_uint(nd.z), rr = __float_as_uint(nd.w);
                     const bool neg = oi.y < 0.f;                           // near = sign[axis], :286
@@ -267,31 +269,15 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace(TraceArgs a) {
                         cur = e.x; rMin = __uint_as_float(e.y); pMin = __uint_as_float(e.z); pMax = __uint_as_float(e.w);
                     } else cur = NONE;
                 }
-            } else if (a.speculate && cur != NONE && post == NONE) {
-                // park the leaf, continue with the next item
-                post = cur & BIH_REF_INDEX; postLo = pMin; postHi = pMax;
-                if (sp > 0) {
-                    sp--;
-                    const uint4 e = stack[sp];
-                    cur = e.x; rMin = __uint_as_float(e.y); pMin = __uint_as_float(e.z); pMax = __uint_as_float(e.w);
-                } else cur = NONE;
             }
-            const uint32_t m_node = __ballot_sync(FULL, (int)cur >= 0);
-            if (m_node == 0) break;
-            if (a.vote) {
-                const uint32_t m_wait = __ballot_sync(FULL, (int)cur < 0 && (cur != NONE || post != NONE) && !(a.speculate && post == NONE));
-                if (a.vote == 1 ? (__popc(m_wait) >= a.leaf_votes)
-                    : a.vote == 2 ? (__popc(m_wait) > __popc(m_node))
-                                  : (m_wait != 0 && __popc(m_node) <= a.leaf_votes)) break;
-            }
+            const uint32_t m_walk = __ballot_sync(FULL, (int)cur >= 0);
+            if (m_walk == 0) break;
+            const uint32_t m_wait = __ballot_sync(FULL, cur + 1u > 0x80000000u);      // a leaf (negative, not NONE)
+            if (__popc(m_wait) * vote_wait > __popc(m_walk) * vote_walk) break;
         }
-        // ================= phase 2: the leaves this lane holds, in traversal order =====================
-        if (post != NONE) {
-            if (postLo <= fminf(postHi, h.t)) test_leaf<COUNTED>(tris, post, ox, oy, oz, dx, dy, dz, h, ntris);
-            post = NONE;
-        }
-        if ((int)cur < 0 && cur != NONE) {
-            if (pMin <= fminf(pMax, h.t)) test_leaf<COUNTED>(tris, cur & BIH_REF_INDEX, ox, oy, oz, dx, dy, dz, h, ntris);
+        // ================= phase 2: the leaf this lane holds ===========================================
+        if (cur + 1u > 0x80000000u) {
+            if (pMin <= fminf(pMax, h.t)) test_leaf<COUNTED>(tris_b + (size_t)(cur & 0x7FFFFFFCu) * 12, ox, oy, oz, dx, dy, dz, h, ntris);
             if (sp > 0) {
                 sp--;
                 const uint4 e = stack[sp];
