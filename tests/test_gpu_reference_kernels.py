@@ -46,6 +46,9 @@ def test_oracle_and_library_match_reference_kernels(renderer, scenes, oracle, na
     for (t, s, what) in ((t_orc, s_orc, "oracle"), (t_lib, s_lib, "library")):
         bad = s != s_ref
         assert bad.sum() <= ID_MISMATCH_MAX * len(rays), "%s: %d of %d ids differ from the reference kernels" % (what, bad.sum(), len(rays))
+        # (ids differ only where a ray grazes a triangle edge: nvcc contracts the reference's glm
+        # expressions into FMAs, the oracle evaluates them uncontracted, so the u/v edge tests can fall
+        # on different sides and the ray continues to the next surface -- the documented tie class)
         hit = ~bad & (s_ref >= 0)
         np.testing.assert_allclose(t[hit], t_ref[hit], rtol=T_REL_TOL, atol=0, err_msg=what)
     ref.close()
