@@ -7,9 +7,10 @@
 Workload (config.workload): the 1 002 528-triangle displaced sphere of BASELINE config 5 (the scene
 the north star's 70 % target is quoted on) seen by the config-2 camera, traced with config 4's ray
 load: 3840x2160 pixels x 16 jittered primary rays = 132 710 400 rays per step.  A step = one frame's
-trace with the BIH resident in HBM.  At N > 1 the frame's 32x32-pixel tiles are dealt round-robin
-over the ranks (strong scaling: total work fixed), the BIH built on rank 0 is replicated by one NCCL
-broadcast before the timed region, and every step ends with the framebuffer reduce to rank 0.
+trace with the BIH resident in HBM.  At N > 1 the frame's rays are partitioned over the ranks (strong
+scaling: total work fixed) -- by sample (rank r traces samples [16r/N, 16(r+1)/N) of every pixel) -- the
+BIH built on rank 0 is replicated by one NCCL broadcast before the timed region, and every step ends
+with the framebuffer reduce to rank 0 (+ resolve of the hit counts to packed colours).
 
 `value`  = rays of the whole frame / max-over-ranks device time (CUDA events on the launching stream).
 `e2e`    = the same metric for the reference's full per-frame sequence through the C ABI with HOST
@@ -39,6 +40,17 @@ L2_FLUSH_BYTES = 256 << 20          # > 126 MB L2
 
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
+
+
+# Exactly ONE line may reach stdout.  Libraries (NCCL prints its version banner there) write to fd 1
+# directly, so fd 1 is pointed at stderr for the whole run and the JSON line goes to a saved copy.
+_REAL_STDOUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(obj):
+    _REAL_STDOUT.write(json.dumps(obj) + "\n")
+    _REAL_STDOUT.flush()
 
 
 def peaks():
@@ -139,7 +151,7 @@ def run_reference(args, rank):
                             "build_ms_per_mtri": build_s * 1e3 / (len(tri) / 1e6)},
            "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -183,13 +195,26 @@ def run_ours(args, rank, world, local_rank):
 
     fb_t = None
 
+    by_sample = world > 1 and spp >= world          # else tiles round-robin
+    s0, s1 = multi.sample_range(spp, rank, world)
+
+    def render_my_share():
+        if world == 1:
+            r.render(cam, W, H, spp=spp, seed=1984, jitter=True)
+        elif by_sample:
+            r.render_samples(cam, W, H, spp, s0, s1, seed=1984, jitter=True)
+        else:
+            r.render(cam, W, H, spp=spp, seed=1984, jitter=True, shard=(rank, world))
+
     def step():
         nonlocal fb_t
-        r.render(cam, W, H, spp=spp, seed=1984, jitter=True, shard=(rank, world))
+        render_my_share()
         if world > 1:
             if fb_t is None:
                 fb_t = multi.framebuffer_tensor(r)
             multi.gather_framebuffer(fb_t, dist, dst=0)
+            if by_sample and rank == 0:
+                r.framebuffer_resolve(spp)
 
     def timed_loop(fn, k):
         """K steps, L2 flushed (untimed) before each, CUDA events on the launching stream; returns
@@ -228,6 +253,14 @@ def run_ours(args, rank, world, local_rank):
     ms = max_over_ranks(ms)
     ms_per_step = ms / args.steps
     value = rays_total / (ms_per_step * 1e-3) / 1e6
+
+    # ---- N > 1: where a step's time goes (diagnostic, separate loop) --------------------------------
+    breakdown = None
+    if world > 1:
+        t_r = max_over_ranks(timed_loop(render_my_share, 3)) / 3
+        t_g = max_over_ranks(timed_loop(lambda: multi.gather_framebuffer(fb_t, dist, dst=0), 3)) / 3
+        breakdown = {"render_shard_ms_max_over_ranks": t_r, "framebuffer_reduce_ms": t_g}
+        barrier()
 
     # ---- e2e: the reference's full frame through the C ABI with host buffers -----------------------
     host_fb = torch.empty((H, W), dtype=torch.int32).pin_memory() if rank == 0 else None
@@ -284,14 +317,17 @@ def run_ours(args, rank, world, local_rank):
                "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                "config": {"workload": name, "triangles": n_tri, "leaves": info["nu"], "rays_per_step": rays_total,
-                          "l2": "flushed before every timed step (256 MiB write)", "parallelism": "tiles%d" % world,
-                          "sharding": "32x32-pixel tiles round-robin over ranks; BIH broadcast once; framebuffer reduce per step"},
+                          "l2": "flushed before every timed step (256 MiB write)", "parallelism": ("samples%d" if by_sample else "tiles%d") % world,
+                          "sharding": ("samples of every pixel split over ranks (hit counts, reduce, resolve)" if by_sample else
+                                       "32x32-pixel tiles round-robin over ranks") + "; BIH broadcast once; framebuffer reduce per step"},
                "build_ms_per_mtri": build_ms / (n_tri / 1e6), "build_ms": build_ms,
                "e2e": {"value": e2e_val, "unit": "Mrays/s", "h2d_bytes_per_step": n_tri * 36, "d2h_bytes_per_step": W * H * 4,
                        "ms_per_step": ms_e2e,
                        "what": "vertices H2D (pinned) + bihrt_build + %sbihrt_render%s + framebuffer D2H (pinned), per frame" % (
                            "BIH broadcast + " if world > 1 else "", " + framebuffer reduce" if world > 1 else "")},
                "gpu_launches": int(launches), "clocks": clocks}
+        if breakdown:
+            out["breakdown"] = breakdown
         if roofline:
             out["roofline"] = roofline
 
@@ -315,7 +351,7 @@ def run_ours(args, rank, world, local_rank):
         out["sizes"] = sizes
         out["cpu_baseline"] = cpu_baseline(args, tri, cam)
     if rank == 0:
-        print(json.dumps(out), flush=True)
+        emit(out)
     r.close()
     if world > 1:
         dist.destroy_process_group()

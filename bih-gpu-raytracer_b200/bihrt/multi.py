@@ -5,9 +5,12 @@ replicated tree, so the partition is data-parallel:
 
   * the BIH is built once on rank `src` and replicated with ONE broadcast of the blob
     [header | nodes | leaf-ordered triangles] (bihrt_bih_export / bihrt_bih_import);
-  * the image's 32x32-pixel tiles are dealt round-robin (tile k -> rank k mod G), each rank renders
-    only its tiles (bihrt_render_shard) and leaves the other pixels 0;
-  * the framebuffer is gathered at the end with ONE reduce (SUM of disjoint shards == gather).
+  * ray batches are partitioned either by SAMPLE (rank r traces samples [spp*r/G, spp*(r+1)/G) of every
+    pixel and stores per-pixel hit counts, bihrt_render_samples -- every rank walks the whole image, so
+    the warps keep the single-GPU coherence; the default when spp >= G) or by TILE (32x32-pixel tiles
+    dealt round-robin, tile k -> rank k mod G, other pixels 0, bihrt_render_shard; used when spp < G);
+  * the framebuffer is gathered at the end with ONE reduce (SUM of counts, or of disjoint shards),
+    followed for sample sharding by bihrt_framebuffer_resolve on the destination rank.
 
 No collective runs during traversal.  The helpers take any torch.distributed backend so the same code
 is exercised with gloo on CPU tensors in tests/test_distributed.py.
@@ -22,6 +25,11 @@ def tile_owner(w, h, world):
     tx = (w + TILE - 1) // TILE
     jj, ii = np.meshgrid(np.arange(h) // TILE, np.arange(w) // TILE, indexing="ij")
     return ((jj * tx + ii) % world).astype(np.int32)
+
+
+def sample_range(spp, rank, world):
+    """Sample sharding: rank -> [begin, end) of the spp samples of every pixel (contiguous, balanced)."""
+    return (spp * rank) // world, (spp * (rank + 1)) // world
 
 
 def shard_ray_count(w, h, spp, rank, world):

@@ -418,8 +418,10 @@ static int render_check(bihrt_ctx* c, const bihrt_camera* cam, int w, int h, int
 }
 
 static int render_impl(bihrt_ctx* c, const bihrt_camera* cam, int32_t w, int32_t h, int32_t spp, uint64_t seed, uint32_t flags,
-                       int32_t shard_index, int32_t shard_count, uint64_t* counters) {
+                       int32_t shard_index, int32_t shard_count, uint64_t* counters, int32_t s_begin = 0, int32_t s_end = -1) {
     ENTER(c);
+    if (s_end < 0) s_end = spp;
+    if (s_begin < 0 || s_begin > s_end || s_end > spp) return bihrt_fail(c, BIHRT_ERR_INVALID, "bad sample range [%d,%d) of %d", s_begin, s_end, spp);
     int rc = render_check(c, cam, w, h, spp, shard_index, shard_count);
     if (rc) return rc;
     const size_t px = (size_t)w * h;
@@ -429,6 +431,11 @@ static int render_impl(bihrt_ctx* c, const bihrt_camera* cam, int32_t w, int32_t
     TraceArgs a; base_args(c, a);
     a.cam = *cam; a.w = w; a.h = h; a.spp = spp; a.seed = seed; a.flags = flags;
     a.shard_index = shard_index; a.shard_count = shard_count; a.fb = c->d_fb;
+    a.s_begin = s_begin; a.s_end = s_end;
+    if (s_begin == s_end) {            // nothing to trace on this rank: all counts are 0
+        BIHRT_CUDA(c, cudaMemsetAsync(c->d_fb, 0, px * 4, c->stream));
+        return BIHRT_OK;
+    }
     if (!counters) return bihrt_trace_launch(c, a, 1, false);
     BIHRT_CUDA(c, cudaMemsetAsync(c->d_counters, 0, 32, c->stream));
     if ((rc = bihrt_trace_launch(c, a, 1, true))) return rc;
@@ -442,6 +449,18 @@ static int render_impl(bihrt_ctx* c, const bihrt_camera* cam, int32_t w, int32_t
 int bihrt_render_shard(bihrt_ctx* c, const bihrt_camera* cam, int32_t w, int32_t h, int32_t spp, uint64_t seed, uint32_t flags,
                        int32_t shard_index, int32_t shard_count) {
     return render_impl(c, cam, w, h, spp, seed, flags, shard_index, shard_count, nullptr);
+}
+
+int bihrt_render_samples(bihrt_ctx* c, const bihrt_camera* cam, int32_t w, int32_t h, int32_t spp, uint64_t seed, uint32_t flags,
+                         int32_t sample_begin, int32_t sample_end) {
+    return render_impl(c, cam, w, h, spp, seed, flags | BIHRT_RENDER_COUNTS, 0, 1, nullptr, sample_begin, sample_end);
+}
+
+int bihrt_framebuffer_resolve(bihrt_ctx* c, int32_t spp) {
+    ENTER(c);
+    if (!c->d_fb) return bihrt_fail(c, BIHRT_ERR_STATE, "nothing rendered yet");
+    if (spp <= 0) return BIHRT_ERR_INVALID;
+    return bihrt_resolve_launch(c, c->d_fb, c->fb_w * c->fb_h, spp);
 }
 
 int bihrt_render_counted(bihrt_ctx* c, const bihrt_camera* cam, int32_t w, int32_t h, int32_t spp, uint64_t seed, uint32_t flags,
@@ -464,6 +483,7 @@ int bihrt_render_hits(bihrt_ctx* c, const bihrt_camera* cam, int32_t w, int32_t 
     if ((rc = stage_outputs(c, n, 0, t, slot, prim, o, &front))) return rc;
     TraceArgs a; base_args(c, a);
     a.cam = *cam; a.w = w; a.h = h; a.spp = spp; a.seed = seed; a.flags = flags;
+    a.s_begin = 0; a.s_end = spp;
     a.out_t = o.t; a.out_slot = o.slot; a.out_prim = o.prim;
     if ((rc = bihrt_trace_launch(c, a, 2, false))) return rc;
     return unstage_outputs(c, n, o);

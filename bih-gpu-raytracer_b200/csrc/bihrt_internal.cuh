@@ -123,6 +123,7 @@ struct TraceArgs {
     float* out_t; int32_t* out_slot; int32_t* out_prim;
     // camera mode
     bihrt_camera cam; int w, h, spp; uint64_t seed; uint32_t flags; int shard_index, shard_count;
+    int s_begin, s_end;     // samples [s_begin, s_end) of every pixel are traced by this launch (of spp in total)
     uint32_t* fb;
     unsigned long long* counters; uint32_t* work;
     int refill_threshold;   // lanes whose ray ended wait until this many are idle (or nobody is busy)
@@ -130,6 +131,7 @@ struct TraceArgs {
     int vote_wait, vote_walk;   // node phase also ends when waiters * vote_wait > walkers * vote_walk (0,x = never)
 };
 int bihrt_trace_launch(bihrt_ctx* c, const TraceArgs& a, int mode /*0 rays,1 render fb,2 render hits*/, bool counted);
+int bihrt_resolve_launch(bihrt_ctx* c, uint32_t* fb, int npix, int spp);
 
 // -------------------------------------------------------------------------------------------
 // device helpers

@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
         const int my_tiles = T > a.shard_index ? (T - a.shard_index + a.shard_count - 1) / a.shard_count : 0;
         total = (uint64_t)my_tiles * 1024u;
     }
-    const int nsamp = MODE == 0 ? 1 : a.spp;
+    const int nsamp = MODE == 0 ? 1 : (a.s_end - a.s_begin);     // samples of each pixel traced by this launch
     uint64_t pool_next = 0, pool_end = 0;      // warp-uniform
     bool exhausted = false;                    // warp-uniform: the global counter ran past `total`
 
@@ -127,14 +127,15 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
                     tracing = false;
                     if (MODE == 1) hits += (h.slot >= 0);
                     else {
-                        const uint64_t o = MODE == 0 ? item : (uint64_t)pixel * (uint32_t)nsamp + (uint32_t)s;
+                        const uint64_t o = MODE == 0 ? item : (uint64_t)pixel * (uint32_t)a.spp + (uint32_t)(a.s_begin + s);
                         if (a.out_t) a.out_t[o] = h.t;
                         if (a.out_slot) a.out_slot[o] = h.slot;
                         if (a.out_prim) a.out_prim[o] = h.slot >= 0 ? (int32_t)tris[h.slot].prim : -1;
                     }
                     s++;
                     if (s == nsamp) {
-                        if (MODE == 1) {
+                        if (MODE == 1 && (a.flags & BIHRT_RENDER_COUNTS)) a.fb[pixel] = hits;     // resolved after the reduce
+                        else if (MODE == 1) {
                             // Color + rgbToInt, R/src/CUDAKernels.cu:82-88,385-387,420-422 (sums of 255/20/40 are exact)
                             const float fh = (float)hits, fm = (float)(nsamp - (int)hits), fs = (float)nsamp;
                             float cr = __fdiv_rn(__fadd_rn(__fmul_rn(fh, 255.f), __fmul_rn(fm, 20.f)), fs);
@@ -186,8 +187,8 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
                 } else {
                     // u,v per R/src/CUDAKernels.cu:414-415; GetRay per R/src/Camera.cu:18-20
                     const int px = (int)(pxy & 0xFFFFu), py = (int)(pxy >> 16);
-                    const float ru = (a.flags & BIHRT_RENDER_JITTER) ? bihrt_jitter(a.seed, pixel, (uint32_t)s, 0) : 0.5f;
-                    const float rv = (a.flags & BIHRT_RENDER_JITTER) ? bihrt_jitter(a.seed, pixel, (uint32_t)s, 1) : 0.5f;
+                    const float ru = (a.flags & BIHRT_RENDER_JITTER) ? bihrt_jitter(a.seed, pixel, (uint32_t)(a.s_begin + s), 0) : 0.5f;
+                    const float rv = (a.flags & BIHRT_RENDER_JITTER) ? bihrt_jitter(a.seed, pixel, (uint32_t)(a.s_begin + s), 1) : 0.5f;
                     const float uu = __fdiv_rn(__fadd_rn((float)px, ru), (float)a.w);
                     const float vv = __fdiv_rn(__fadd_rn((float)py, rv), (float)a.h);
                     ox = a.cam.origin[0]; oy = a.cam.origin[1]; oz = a.cam.origin[2];
@@ -300,6 +301,26 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
             atomicMax(&a.counters[2], (unsigned long long)maxsp);
         }
     }
+}
+
+// hit counts -> packed colour (Color + rgbToInt, R/src/CUDAKernels.cu:82-88,385-387,420-422), in place
+__global__ void k_resolve(uint32_t* fb, int npix, int spp) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix) return;
+    const uint32_t hits = fb[i];
+    const float fh = (float)hits, fm = (float)(spp - (int)hits), fs = (float)spp;
+    float cr = __fdiv_rn(__fadd_rn(__fmul_rn(fh, 255.f), __fmul_rn(fm, 20.f)), fs);
+    float cb = __fdiv_rn(__fmul_rn(fm, 40.f), fs);
+    cr = fmaxf(0.f, fminf(255.f, cr));
+    cb = fmaxf(0.f, fminf(255.f, cb));
+    fb[i] = ((uint32_t)(int)cb << 16) | ((uint32_t)(int)cr << 8) | (uint32_t)(int)cr;
+}
+
+int bihrt_resolve_launch(bihrt_ctx* c, uint32_t* fb, int npix, int spp) {
+    k_resolve<<<(npix + 255) / 256, 256, 0, c->stream>>>(fb, npix, spp);
+    c->kernel_launches += 1;
+    BIHRT_CUDA(c, cudaGetLastError());
+    return BIHRT_OK;
 }
 
 template <int MODE, bool COUNTED>

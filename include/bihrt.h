@@ -67,6 +67,7 @@ typedef struct bihrt_ray {
 
 /* bihrt_render flags */
 #define BIHRT_RENDER_JITTER   1u   /* jittered samples (reference behaviour); otherwise pixel centres */
+#define BIHRT_RENDER_COUNTS   2u   /* framebuffer receives per-pixel hit counts instead of packed colours */
 
 /* Reference view of a built BIH: arrays with the exact field meaning of the reference's device
  * arrays.  Caller allocates; any pointer may be NULL to skip that array.
@@ -148,6 +149,13 @@ BIHRT_API int bihrt_render_counted(bihrt_ctx* ctx, const bihrt_camera* cam, int3
  * is the full image. */
 BIHRT_API int bihrt_render_shard(bihrt_ctx* ctx, const bihrt_camera* cam, int32_t w, int32_t h, int32_t spp,
                        uint64_t seed, uint32_t flags, int32_t shard_index, int32_t shard_count);
+/* Multi-GPU, sample sharding: trace only samples [sample_begin, sample_end) of every pixel of a
+ * spp-sample frame and store per-pixel HIT COUNTS in the framebuffer.  Summing the counts of all ranks
+ * and calling bihrt_framebuffer_resolve(spp) gives exactly the image bihrt_render(spp) produces; every
+ * rank walks the whole image, so warp coherence is that of the single-GPU render. */
+BIHRT_API int bihrt_render_samples(bihrt_ctx* ctx, const bihrt_camera* cam, int32_t w, int32_t h, int32_t spp,
+                         uint64_t seed, uint32_t flags, int32_t sample_begin, int32_t sample_end);
+BIHRT_API int bihrt_framebuffer_resolve(bihrt_ctx* ctx, int32_t spp);   /* counts -> packed colours, in place */
 /* Per-sample hit buffers of the same rays bihrt_render traces (index = (j*w+i)*spp + s); device or
  * host outputs, any may be NULL.  Used by the parity tests. */
 BIHRT_API int bihrt_render_hits(bihrt_ctx* ctx, const bihrt_camera* cam, int32_t w, int32_t h, int32_t spp,

@@ -137,6 +137,20 @@ def test_render_hits_framebuffer_and_shards(renderer, scenes, oracle):
         assert np.all((acc == 0) | (part == 0))
         acc += part
     np.testing.assert_array_equal(acc, full)
+    # sample shards: per-pixel hit counts of disjoint sample ranges; sum + resolve == full image
+    from bihrt import multi
+    import torch
+    counts = torch.zeros((h, w), dtype=torch.int32, device="cuda")
+    for k in range(3):
+        s0, s1 = multi.sample_range(spp, k, 3)
+        renderer.render_samples(cam, w, h, spp, s0, s1, jitter=True)
+        renderer.sync()                                   # the library runs on its own stream here
+        counts += multi.framebuffer_tensor(renderer)
+        torch.cuda.synchronize()
+    assert int(counts.max()) <= spp
+    multi.framebuffer_tensor(renderer).copy_(counts)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(renderer.framebuffer_resolve(spp).framebuffer(), full)
 
 
 def test_bih_blob_roundtrip(scenes, oracle):
