@@ -68,7 +68,7 @@ static int ensure_capacity(bihrt_ctx* c, int64_t n, bool with_build_scratch) {
         c->blob_cap = blob_capacity(cap);
         dev_free(&c->d_tri_in);
         for (int i = 0; i < 2; i++) { dev_free(&c->d_keys[i]); dev_free(&c->d_vals[i]); }
-        dev_free(&c->d_umc); dev_free(&c->d_first); dev_free(&c->d_lookback); dev_free(&c->d_arrive); dev_free(&c->d_boxscratch);
+        dev_free(&c->d_umc); dev_free(&c->d_first); dev_free(&c->d_lookback); dev_free(&c->d_heaps);
         c->cap_n = cap;
         c->have_scene = false; c->built = false;
         bind_blob(c, cap);
@@ -84,8 +84,9 @@ static int ensure_capacity(bihrt_ctx* c, int64_t n, bool with_build_scratch) {
         if ((rc = dev_alloc(c, &c->d_first, (size_t)cap + 8))) return rc;
         c->lookback_words = lookback_words_for(cap);
         if ((rc = dev_alloc(c, &c->d_lookback, c->lookback_words))) return rc;
-        if ((rc = dev_alloc(c, &c->d_arrive, (size_t)cap + 8))) return rc;
-        if ((rc = dev_alloc(c, &c->d_boxscratch, (size_t)cap * 16 + 16))) return rc;
+        size_t P = 256;
+        while (P < (size_t)cap) P <<= 1;
+        if ((rc = dev_alloc(c, &c->d_heaps, 12 * P))) return rc;
     }
     return BIHRT_OK;
 }
@@ -127,11 +128,12 @@ void bihrt_destroy(bihrt_ctx* c) {
     dev_free(&c->d_tri_in); dev_free(&c->d_blob);
     for (int i = 0; i < 2; i++) { dev_free(&c->d_keys[i]); dev_free(&c->d_vals[i]); }
     dev_free(&c->d_umc); dev_free(&c->d_first); dev_free(&c->d_hist); dev_free(&c->d_lookback);
-    dev_free(&c->d_arrive); dev_free(&c->d_boxscratch); dev_free(&c->d_scenebox_enc);
+    dev_free(&c->d_heaps); dev_free(&c->d_scenebox_enc);
     dev_free(&c->d_fb); dev_free(&c->d_counters); dev_free(&c->d_work);
     if (c->d_io) { cudaFree(c->d_io); c->d_io = nullptr; }
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    for (int i = 0; i < BIHRT_PROF_EVENTS; i++) if (c->prof_ev[i]) cudaEventDestroy(c->prof_ev[i]);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -156,6 +158,10 @@ int bihrt_set_option(bihrt_ctx* c, const char* name, int64_t v) {
     if (!strcmp(name, "trace_blocks_per_sm")) c->opt_trace_blocks_per_sm = (int)v;
     else if (!strcmp(name, "trace_variant")) c->opt_trace_variant = (int)v;
     else if (!strcmp(name, "trace_refill_threshold")) c->opt_refill_threshold = (int)std::max<int64_t>(1, std::min<int64_t>(32, v));
+    else if (!strcmp(name, "profile")) {
+        c->opt_profile = (int)v;
+        if (v) for (int i = 0; i < BIHRT_PROF_EVENTS; i++) if (!c->prof_ev[i]) cudaEventCreate(&c->prof_ev[i]);
+    }
     else if (!strcmp(name, "trace_vote_wait")) c->opt_vote_wait = (int)v;
     else if (!strcmp(name, "trace_vote_walk")) c->opt_vote_walk = (int)v;
     else if (!strcmp(name, "trace_chunk_items")) c->opt_chunk_items = (int)std::max<int64_t>(32, (v + 31) / 32 * 32);
@@ -166,6 +172,15 @@ int bihrt_set_option(bihrt_ctx* c, const char* name, int64_t v) {
 int bihrt_get_stat(bihrt_ctx* c, const char* name, int64_t* v) {
     if (!c || !name || !v) return BIHRT_ERR_INVALID;
     if (!strcmp(name, "kernel_launches")) *v = c->kernel_launches;
+    else if (!strncmp(name, "build_stage_ns_", 15)) {
+        // stages: 0 init+memsets, 1 scene_box, 2 morton, 3-6 sort passes, 7 rle, 8 reorder + slot boxes, 9 upper heap levels, 10 nodes
+        const int i = atoi(name + 15);
+        if (!c->opt_profile || i < 0 || i + 1 >= c->prof_count) return bihrt_fail(c, BIHRT_ERR_STATE, "no profile for stage %d (set option profile=1 and build)", i);
+        BIHRT_CUDA(c, cudaEventSynchronize(c->prof_ev[i + 1]));
+        float ms = 0;
+        BIHRT_CUDA(c, cudaEventElapsedTime(&ms, c->prof_ev[i], c->prof_ev[i + 1]));
+        *v = (int64_t)(ms * 1e6f);
+    }
     else return bihrt_fail(c, BIHRT_ERR_INVALID, "unknown stat '%s'", name);
     return BIHRT_OK;
 }

@@ -60,6 +60,7 @@ static_assert(sizeof(BihHeader) == 64, "header is one 64-byte line");
 // -------------------------------------------------------------------------------------------
 // context
 // -------------------------------------------------------------------------------------------
+#define BIHRT_PROF_EVENTS 16
 struct bihrt_ctx {
     int          device = 0;
     cudaStream_t stream = nullptr;
@@ -86,8 +87,7 @@ struct bihrt_ctx {
     uint32_t *d_hist = nullptr;       // 4 x 256 digit histograms + tile counters + misc
     uint32_t *d_lookback = nullptr;   // onesweep / RLE decoupled look-back words
     size_t    lookback_words = 0;
-    int32_t  *d_arrive = nullptr;     // agglomerative build: other child's range end, -1 = nobody yet
-    float    *d_boxscratch = nullptr; // 6 floats per split
+    float    *d_heaps = nullptr;      // six implicit min/max heaps over the leaf boxes, 2P floats each
     uint32_t *d_scenebox_enc = nullptr; // 6 order-preserving encoded floats
 
     // trace
@@ -108,6 +108,9 @@ struct bihrt_ctx {
     int opt_vote_wait = 1, opt_vote_walk = 1;
     int opt_sort_passes = 4;
     int64_t kernel_launches = 0;
+    int opt_profile = 0;    // record an event after every build stage (bihrt_get_stat "build_stage_us_<i>")
+    cudaEvent_t prof_ev[BIHRT_PROF_EVENTS] = {};
+    int prof_count = 0;
 };
 
 int  bihrt_fail(bihrt_ctx* c, int code, const char* fmt, ...);

@@ -8,10 +8,12 @@
 //   k_scene_box   scene AABB                                   36 B read per triangle
 //   k_morton      AABB centre -> 30-bit Morton key, fused 4x256 digit histogram   36 R + 4 W
 //   k_onesweep x4 stable LSD radix sort, 8-bit digits, decoupled look-back       16 R + 16 W per pass
-//   k_rle         head flags -> unique codes, first slot of each leaf, Nu          4 R + <=8 W
-//   k_tree        per leaf: gather + reorder triangles (36 R + 48 W), leaf AABB, then bottom-up
-//                 agglomerative radix-tree construction that emits each node ONCE, in the reference's
-//                 node numbering, with both clip planes                           ~64 R/W scratch + 16 W
+//   k_rle_*       head flags -> unique codes, first slot of each leaf, Nu (count, scan, write)  8 R + <=8 W
+//   k_reorder     per slot: gather the triangle, write its 48-byte leaf-ordered record and its AABB as the
+//                 bottom level of six implicit min/max heaps (+8 levels per block)   4+36 R + 48+~48 W
+//   k_heap_up     upper heap levels (8 per launch)
+//   k_nodes       per node: Karras range/split search + two heap range queries for the clip planes,
+//                 each node written once                                            ~40 R + 16 W
 // Results are bit-identical to the reference algorithm (oracle/bih_oracle.c): the radix tree over the
 // unique sorted codes is unique, node ids follow the Karras numbering rule, clip planes are pure
 // max/min of input floats.
@@ -42,14 +44,15 @@ __device__ __forceinline__ uint32_t block_excl_scan_256(uint32_t v, uint32_t* s_
     return base + inc - v;
 }
 
-// Stage `cnt` (<=256) triangles starting at triangle `base` (multiple of 256) into shared memory
-// with coalesced 128-bit loads; thread t then reads its 9 floats at s[9*t] (stride 9: conflict-free).
-__device__ __forceinline__ void stage_tris_256(const float* __restrict__ tri, uint32_t base, uint32_t cnt, float* s) {
-    const float4* src = reinterpret_cast<const float4*>(tri + (size_t)base * 9);
-    uint32_t nfl = cnt * 9, nv4 = nfl >> 2;
-    for (uint32_t i = threadIdx.x; i < nv4; i += 256) reinterpret_cast<float4*>(s)[i] = __ldcs(src + i);
-    for (uint32_t i = (nv4 << 2) + threadIdx.x; i < nfl; i += 256) s[i] = tri[(size_t)base * 9 + i];
-    __syncthreads();
+// The streaming kernels read the input 4 triangles (36 floats = 9 x 16 B, 144 B, 16-byte aligned) per
+// thread with nine independent 128-bit loads in flight; a warp covers 4.6 KB contiguous per iteration.
+__device__ __forceinline__ void load_quad(const float* __restrict__ tri, uint32_t q, float v[36]) {
+    const float4* p = reinterpret_cast<const float4*>(tri) + (size_t)q * 9;
+#pragma unroll
+    for (int i = 0; i < 9; i++) {
+        const float4 f = __ldcs(p + i);
+        v[4 * i] = f.x; v[4 * i + 1] = f.y; v[4 * i + 2] = f.z; v[4 * i + 3] = f.w;
+    }
 }
 
 // std::minmax({a,b,c}) of R/src/App.cpp:123-125: leftmost minimum, rightmost maximum under <.
@@ -78,19 +81,18 @@ __global__ void k_init(uint32_t* hist, uint32_t* enc, BihHeader* hdr, uint32_t n
 // std::minmax order dependence; it cannot change any Morton code or hit.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_scene_box(const float* __restrict__ tri, uint32_t n, uint32_t* __restrict__ enc) {
-    __shared__ __align__(16) float s[256 * 9];
     float lo[3] = { INFINITY, INFINITY, INFINITY }, hi[3] = { -INFINITY, -INFINITY, -INFINITY };
-    for (uint32_t base = blockIdx.x * 256u; base < n; base += gridDim.x * 256u) {
-        uint32_t cnt = min(256u, n - base);
-        stage_tris_256(tri, base, cnt, s);
-        if (threadIdx.x < cnt) {
-            const float* t = s + 9 * threadIdx.x;
+    const uint32_t nq = n >> 2;
+    for (uint32_t q = blockIdx.x * 256u + threadIdx.x; q < nq; q += gridDim.x * 256u) {
+        float v[36];
+        load_quad(tri, q, v);
 #pragma unroll
-            for (int v = 0; v < 3; v++)
-#pragma unroll
-                for (int k = 0; k < 3; k++) { float f = t[3 * v + k]; lo[k] = fminf(lo[k], f); hi[k] = fmaxf(hi[k], f); }
-        }
-        __syncthreads();
+        for (int i = 0; i < 36; i++) { lo[i % 3] = fminf(lo[i % 3], v[i]); hi[i % 3] = fmaxf(hi[i % 3], v[i]); }
+    }
+    if (blockIdx.x == 0 && threadIdx.x < 9u * (n & 3u)) {           // the last n % 4 triangles
+        const float f = tri[(size_t)nq * 36 + threadIdx.x];
+        const int k = threadIdx.x % 3;
+        lo[k] = fminf(lo[k], f); hi[k] = fmaxf(hi[k], f);
     }
 #pragma unroll
     for (int k = 0; k < 3; k++) {
@@ -100,11 +102,21 @@ __global__ void __launch_bounds__(256) k_scene_box(const float* __restrict__ tri
             hi[k] = fmaxf(hi[k], __shfl_xor_sync(FULL, hi[k], o));
         }
     }
+    // block-level reduction first: 6 atomics per block instead of per warp (they all hit 6 words)
+    __shared__ float s_red[8][6];
+    const int w = threadIdx.x >> 5;
     if ((threadIdx.x & 31) == 0) {
 #pragma unroll
-        for (int k = 0; k < 3; k++) { atomicMin(&enc[k], enc_float(lo[k])); atomicMax(&enc[3 + k], enc_float(hi[k])); }
+        for (int k = 0; k < 3; k++) { s_red[w][k] = lo[k]; s_red[w][3 + k] = hi[k]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        float r = s_red[0][threadIdx.x];
+        for (int i = 1; i < 8; i++) r = threadIdx.x < 3 ? fminf(r, s_red[i][threadIdx.x]) : fmaxf(r, s_red[i][threadIdx.x]);
+        if (threadIdx.x < 3) atomicMin(&enc[threadIdx.x], enc_float(r)); else atomicMax(&enc[threadIdx.x], enc_float(r));
     }
 }
+
 
 // ------------------------------------------------------------------------------------------
 // Morton keys (R/src/App.cpp:128-131,144-156 + R/src/Renderer.cpp:116-136) + digit histograms
@@ -117,15 +129,32 @@ __device__ __forceinline__ uint32_t expand_bits10(uint32_t v) {
     return v;
 }
 __device__ __forceinline__ uint32_t morton_axis(float mn, float mx, float slo, float shi) {
-    float centre = __fdiv_rn(__fadd_rn(mn, mx), 2.0f);
+    float centre = __fmul_rn(__fadd_rn(mn, mx), 0.5f);    // == (mn + mx) / 2.0f exactly (scaling by a power of two)
     float nrm = __fdiv_rn(__fsub_rn(centre, slo), __fsub_rn(shi, slo));
     float q = fminf(fmaxf(__fmul_rn(nrm, 1024.0f), 0.0f), 1023.0f);   // fmaxf(NaN,0)=0: flat axis -> cell 0
     return expand_bits10(__float2uint_rz(q));
 }
 
+__device__ __forceinline__ uint32_t morton_of_tri(const float* t, const float slo[3], const float shi[3]) {
+    float mn, mx;
+    minmax3(t[0], t[3], t[6], mn, mx); const uint32_t xx = morton_axis(mn, mx, slo[0], shi[0]);
+    minmax3(t[1], t[4], t[7], mn, mx); const uint32_t yy = morton_axis(mn, mx, slo[1], shi[1]);
+    minmax3(t[2], t[5], t[8], mn, mx); const uint32_t zz = morton_axis(mn, mx, slo[2], shi[2]);
+    return xx * 4 + yy * 2 + zz;
+}
+
+// warp-aggregated histogram update: coherent meshes put whole warps into one bin
+__device__ __forceinline__ void hist_add(uint32_t* s_hist, uint32_t code, uint32_t act, int lane) {
+#pragma unroll
+    for (int p = 0; p < 4; p++) {
+        const uint32_t d = (code >> (8 * p)) & 255u;
+        const uint32_t peers = __match_any_sync(act, d);
+        if (lane == __ffs(peers) - 1) atomicAdd(&s_hist[p * 256 + d], __popc(peers));
+    }
+}
+
 __global__ void __launch_bounds__(256) k_morton(const float* __restrict__ tri, uint32_t n, const uint32_t* __restrict__ enc,
                                                 uint32_t* __restrict__ keys, uint32_t* __restrict__ hist, BihHeader* hdr) {
-    __shared__ __align__(16) float s[256 * 9];
     __shared__ uint32_t s_hist[4 * 256];
     for (int i = threadIdx.x; i < 1024; i += 256) s_hist[i] = 0;
     float slo[3], shi[3];
@@ -135,32 +164,36 @@ __global__ void __launch_bounds__(256) k_morton(const float* __restrict__ tri, u
 #pragma unroll
         for (int k = 0; k < 3; k++) { hdr->lo[k] = slo[k]; hdr->hi[k] = shi[k]; }
     }
+    __syncthreads();
     const int lane = threadIdx.x & 31;
-    for (uint32_t base = blockIdx.x * 256u; base < n; base += gridDim.x * 256u) {
-        uint32_t cnt = min(256u, n - base);
-        stage_tris_256(tri, base, cnt, s);      // its __syncthreads also orders the s_hist zeroing
-        bool valid = threadIdx.x < cnt;
-        uint32_t code = 0;
+    const uint32_t nq = n >> 2;
+    // warp-uniform trip count so the match_any masks are well defined
+    for (uint32_t q0 = blockIdx.x * 256u + (threadIdx.x & ~31u); q0 < nq; q0 += gridDim.x * 256u) {
+        const uint32_t q = q0 + lane;
+        const bool valid = q < nq;
+        const uint32_t act = __ballot_sync(FULL, valid);
         if (valid) {
-            const float* t = s + 9 * threadIdx.x;
-            float mn, mx;
-            minmax3(t[0], t[3], t[6], mn, mx); uint32_t xx = morton_axis(mn, mx, slo[0], shi[0]);
-            minmax3(t[1], t[4], t[7], mn, mx); uint32_t yy = morton_axis(mn, mx, slo[1], shi[1]);
-            minmax3(t[2], t[5], t[8], mn, mx); uint32_t zz = morton_axis(mn, mx, slo[2], shi[2]);
-            code = xx * 4 + yy * 2 + zz;
-            keys[base + threadIdx.x] = code;
+            float v[36];
+            load_quad(tri, q, v);
+            uint4 c;
+            c.x = morton_of_tri(v, slo, shi); c.y = morton_of_tri(v + 9, slo, shi);
+            c.z = morton_of_tri(v + 18, slo, shi); c.w = morton_of_tri(v + 27, slo, shi);
+            *reinterpret_cast<uint4*>(keys + (size_t)q * 4) = c;
+            hist_add(s_hist, c.x, act, lane); hist_add(s_hist, c.y, act, lane);
+            hist_add(s_hist, c.z, act, lane); hist_add(s_hist, c.w, act, lane);
         }
-        // warp-aggregated histogram: coherent meshes put whole warps into one bin
-        uint32_t act = __ballot_sync(FULL, valid);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < 32) {                      // the last n % 4 triangles
+        const bool valid = (uint32_t)lane < (n & 3u);
+        const uint32_t act = __ballot_sync(FULL, valid);
         if (valid) {
+            float t[9];
 #pragma unroll
-            for (int p = 0; p < 4; p++) {
-                uint32_t d = (code >> (8 * p)) & 255u;
-                uint32_t peers = __match_any_sync(act, d);
-                if (lane == __ffs(peers) - 1) atomicAdd(&s_hist[p * 256 + d], __popc(peers));
-            }
+            for (int i = 0; i < 9; i++) t[i] = tri[((size_t)nq * 4 + lane) * 9 + i];
+            const uint32_t code = morton_of_tri(t, slo, shi);
+            keys[(size_t)nq * 4 + lane] = code;
+            hist_add(s_hist, code, act, lane);
         }
-        __syncthreads();
     }
     __syncthreads();
     for (int i = threadIdx.x; i < 1024; i += 256) { uint32_t v = s_hist[i]; if (v) atomicAdd(&hist[H_HIST + i], v); }
@@ -285,65 +318,78 @@ __global__ void __launch_bounds__(OS_THREADS) k_onesweep(const uint32_t* __restr
 // ------------------------------------------------------------------------------------------
 // Run-length encoding of the sorted keys: unique codes, first slot of every leaf, Nu
 // (replaces thrust::reduce_by_key + thrust::unique_by_key_copy, R/src/Renderer.cpp:450-472;
-// duplicatesCnts[k] = first[k+1] - first[k]).  Single sweep, look-back on one word per tile.
+// duplicatesCnts[k] = first[k+1] - first[k]).  Reduce-then-scan: count heads per tile, scan the tile
+// counts in one block, write.  (A chained look-back over thousands of 8 KB tiles serialises on L2 round
+// trips; the second read of the keys comes from L2.)  Nu stays on the device.
 // ------------------------------------------------------------------------------------------
 #define RLE_ITEMS 8
 #define RLE_TILE  (256 * RLE_ITEMS)
 
-__global__ void __launch_bounds__(256) k_rle(const uint32_t* __restrict__ keys, uint32_t n, uint32_t* __restrict__ umc,
-                                             uint32_t* __restrict__ first, uint32_t* __restrict__ hist,
-                                             uint32_t* __restrict__ lookback, BihHeader* hdr) {
-    __shared__ uint32_t s_w[8];
-    __shared__ uint32_t s_tile, s_excl;
-    const int tid = threadIdx.x;
-    if (tid == 0) s_tile = atomicAdd(&hist[H_TILECTR + 4], 1u);
-    __syncthreads();
-    const uint32_t tile = s_tile;
-    const uint32_t ntiles = (n + RLE_TILE - 1) / RLE_TILE;
-    const uint32_t g0 = tile * RLE_TILE + tid * RLE_ITEMS;
-    uint32_t key[RLE_ITEMS];
+__device__ __forceinline__ uint32_t rle_heads(const uint32_t* __restrict__ keys, uint32_t n, uint32_t g0, uint32_t key[RLE_ITEMS], uint32_t& cnt) {
     if (g0 + RLE_ITEMS <= n) {
-        uint4 a = *reinterpret_cast<const uint4*>(keys + g0), b = *reinterpret_cast<const uint4*>(keys + g0 + 4);
+        const uint4 a = *reinterpret_cast<const uint4*>(keys + g0), b = *reinterpret_cast<const uint4*>(keys + g0 + 4);
         key[0] = a.x; key[1] = a.y; key[2] = a.z; key[3] = a.w; key[4] = b.x; key[5] = b.y; key[6] = b.z; key[7] = b.w;
     } else {
 #pragma unroll
         for (int i = 0; i < RLE_ITEMS; i++) key[i] = (g0 + i < n) ? keys[g0 + i] : 0u;
     }
     uint32_t prev = (g0 > 0 && g0 < n) ? keys[g0 - 1] : 0u;
-    uint32_t heads = 0, cnt = 0;
+    uint32_t heads = 0;
+    cnt = 0;
 #pragma unroll
     for (int i = 0; i < RLE_ITEMS; i++) {
-        uint32_t gi = g0 + i;
-        bool h = (gi < n) && (gi == 0 || key[i] != prev);
+        const uint32_t gi = g0 + i;
+        const bool h = (gi < n) && (gi == 0 || key[i] != prev);
         prev = key[i];
         heads |= (h ? 1u : 0u) << i;
         cnt += h;
     }
-    uint32_t total;
-    uint32_t toff = block_excl_scan_256(cnt, s_w, &total);
-    if (tid == 0) {
-        uint32_t excl = 0;
-        if (tile == 0) {
-            st_relaxed(lookback, total | LB_FLAG_INCL);
-        } else {
-            st_relaxed(lookback + tile, total | LB_FLAG_AGG);
-            const uint32_t* p = lookback + tile - 1;
-            uint32_t spins = 0;
-            for (;;) {
-                uint32_t v = ld_relaxed(p);
-                uint32_t f = v & ~LB_MASK;
-                if (f == 0) { if (++spins > SPIN_LIMIT) { atomicOr(&hdr->status, 2u); break; } continue; }
-                excl += v & LB_MASK;
-                if (f == LB_FLAG_INCL) break;
-                p -= 1;
-            }
-            st_relaxed(lookback + tile, (excl + total) | LB_FLAG_INCL);
-        }
-        s_excl = excl;
-        if (tile == ntiles - 1) { uint32_t nu = excl + total; hdr->nu = nu; first[nu] = n; }
-    }
+    return heads;
+}
+
+__global__ void __launch_bounds__(256) k_rle_count(const uint32_t* __restrict__ keys, uint32_t n, uint32_t* __restrict__ tile_cnt) {
+    __shared__ uint32_t s_w[8];
+    uint32_t key[RLE_ITEMS], cnt;
+    rle_heads(keys, n, blockIdx.x * RLE_TILE + threadIdx.x * RLE_ITEMS, key, cnt);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(FULL, cnt, o);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = cnt;
     __syncthreads();
-    uint32_t k = s_excl + toff;
+    if (threadIdx.x == 0) { uint32_t t = 0; for (int i = 0; i < 8; i++) t += s_w[i]; tile_cnt[blockIdx.x] = t; }
+}
+
+// exclusive scan of the tile counts in place (one block), Nu and the sentinel first[Nu] = n
+__global__ void __launch_bounds__(1024) k_rle_scan(uint32_t* __restrict__ tile_cnt, uint32_t ntiles, uint32_t n,
+                                                   uint32_t* __restrict__ first, BihHeader* hdr) {
+    __shared__ uint32_t s_w[32];
+    __shared__ uint32_t s_carry;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < ntiles; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < ntiles ? tile_cnt[i] : 0u;
+        uint32_t inc = warp_incl_scan(v, lane);
+        if (lane == 31) s_w[w] = inc;
+        __syncthreads();
+        if (w == 0) { uint32_t x = s_w[lane]; uint32_t xi = warp_incl_scan(x, lane); s_w[lane] = xi - x; }
+        __syncthreads();
+        const uint32_t excl = s_carry + s_w[w] + inc - v;
+        if (i < ntiles) tile_cnt[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { const uint32_t nu = s_carry; hdr->nu = nu; first[nu] = n; }
+}
+
+__global__ void __launch_bounds__(256) k_rle_write(const uint32_t* __restrict__ keys, uint32_t n, const uint32_t* __restrict__ tile_off,
+                                                   uint32_t* __restrict__ umc, uint32_t* __restrict__ first) {
+    __shared__ uint32_t s_w[8];
+    const uint32_t g0 = blockIdx.x * RLE_TILE + threadIdx.x * RLE_ITEMS;
+    uint32_t key[RLE_ITEMS], cnt, total;
+    const uint32_t heads = rle_heads(keys, n, g0, key, cnt);
+    uint32_t k = tile_off[blockIdx.x] + block_excl_scan_256(cnt, s_w, &total);
 #pragma unroll
     for (int i = 0; i < RLE_ITEMS; i++) {
         if (heads & (1u << i)) { umc[k] = key[i]; first[k] = g0 + i; k++; }
@@ -351,111 +397,151 @@ __global__ void __launch_bounds__(256) k_rle(const uint32_t* __restrict__ keys, 
 }
 
 // ------------------------------------------------------------------------------------------
-// Leaves + tree.  One thread per leaf (unique Morton cell):
-//   1. gather the leaf's triangles in sorted order, write the 48-byte leaf-ordered records, and take
-//      the union of their AABBs (FindClipPlanes' first loop, R/src/CUDAKernels.cu:511-529);
-//   2. climb: bottom-up agglomerative construction of the binary radix tree over the unique codes.
-//      A range [l,r] of leaves joins the neighbour it shares the longer Morton prefix with; the second
-//      child to arrive at a split owns the new node.  That yields exactly the tree BuildTree's
-//      per-node binary searches find (R/src/CUDAKernels.cu:591-710) -- the radix tree of a sorted set
-//      of distinct keys is unique -- and each node is written once, with both clip planes
-//      (clip0 = max hi[axis] of the left subtree, clip1 = min lo[axis] of the right subtree), instead
-//      of O(depth) float atomics per leaf that all meet at the root (R/src/CUDAKernels.cu:532-547).
-//   Node numbering = the reference's: a node covering leaves [a,b] is stored at index b if it is a left
-//   child, a if it is a right child, 0 for the root, so node i here IS
-//   TreeInternalNode i there.
+// Leaves, tree and clip planes without any inter-thread dependency:
+//   k_reorder     thread per sorted slot: the triangle's AABB becomes the bottom level of six implicit binary
+//                 heaps (max-heaps of hi.xyz, min-heaps of lo.xyz over the triangles in sorted order); each
+//                 block also reduces its 256 slots through 8 heap levels.  A leaf (unique Morton cell) is
+//                 the slot range [first[k], first[k+1]), so FindClipPlanes' per-leaf union loop
+//                 (R/src/CUDAKernels.cu:511-529) is part of the range query below.
+//   k_heap_up     the remaining heap levels, 8 per launch.
+//   k_nodes       thread per internal node i: range [a,b] and split by the same neighbour-prefix
+//                 searches as the reference's BuildTree (R/src/CUDAKernels.cu:591-710) -- so node i is
+//                 TreeInternalNode i by construction -- then the two clip planes as RANGE QUERIES on the
+//                 heaps: clip0 = max hi[axis] over the slots of leaves [a, split], clip1 = min lo[axis] over
+//                 those of [split+1, b].  max/min of the same input floats as the reference's float atomics
+//                 (:52-66,532-547), hence bit-identical, but O(log range) independent loads per node
+//                 instead of O(depth) atomics per leaf that all meet at the root, and no chain of
+//                 fences/atomics between threads (a bottom-up climb serialises on ~depth L2 round trips).
 // ------------------------------------------------------------------------------------------
 struct Box { float lo[3], hi[3]; };
 
-__device__ __forceinline__ float pick(const float v[3], int axis) { return axis == 0 ? v[0] : (axis == 1 ? v[1] : v[2]); }
+// heap c (0..2: max-heap of hi[c]; 3..5: min-heap of lo[c-3]) lives at heaps + c * 2P; element 1 is the
+// root, the per-slot triangle boxes sit at [P, 2P).  Entries whose subtree holds no slot below n are never
+// read by a range query inside [0, n) and are left unwritten.
 
-__global__ void __launch_bounds__(128) k_tree(const float* __restrict__ tri_in, const uint32_t* __restrict__ idx_sorted,
-                                              const uint32_t* __restrict__ umc, const uint32_t* __restrict__ first,
-                                              BihHeader* hdr, BihNode* __restrict__ nodes,
-                                              BihTri* __restrict__ tris, int32_t* __restrict__ arrive,
-                                              float4* __restrict__ boxscratch) {
-    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t nu = hdr->nu;
-    if (k >= nu) return;
-    const uint32_t s0 = first[k], s1 = first[k + 1];
-    Box box;
-    for (uint32_t j = s0; j < s1; j++) {
+// One block reduces 256 consecutive elements of the level that starts at heap index `in_base` through
+// up to 8 further levels (s[][] holds the 256 inputs on entry).
+__device__ __forceinline__ void heap_reduce_block(float (*s)[256], float* __restrict__ heaps, uint32_t P, uint32_t in_base) {
+    uint32_t width = 128, level_base = in_base >> 1;
+    for (; level_base >= 1; width >>= 1, level_base >>= 1) {
+        __syncthreads();
+        float r[6];
+        const bool act = threadIdx.x < width && (blockIdx.x * width + threadIdx.x) < level_base;
+        if (act) {
+#pragma unroll
+            for (int c = 0; c < 6; c++) {
+                const float x = s[c][2 * threadIdx.x], y = s[c][2 * threadIdx.x + 1];
+                r[c] = c < 3 ? fmaxf(x, y) : fminf(x, y);
+            }
+        }
+        __syncthreads();
+        if (act) {
+#pragma unroll
+            for (int c = 0; c < 6; c++) {
+                s[c][threadIdx.x] = r[c];
+                heaps[(size_t)c * 2 * P + level_base + blockIdx.x * width + threadIdx.x] = r[c];
+            }
+        }
+        if (width == 1) break;
+    }
+}
+
+// Leaf-ordered triangle records + bottom heap levels: one thread per sorted slot gathers its input triangle
+// (36 B), writes the 48-byte record (coalesced) and the triangle's AABB (std::minmax semantics of
+// R/src/App.cpp:123-127) as heap level 0.  end-of-leaf = the next slot has a different Morton code.
+__global__ void __launch_bounds__(256) k_reorder(const float* __restrict__ tri_in, const uint32_t* __restrict__ idx_sorted,
+                                                 const uint32_t* __restrict__ keys_sorted, uint32_t n, BihTri* __restrict__ tris,
+                                                 float* __restrict__ heaps, uint32_t P) {
+    __shared__ float s[6][256];
+    const uint32_t j = blockIdx.x * 256u + threadIdx.x;
+    float mn[3] = { INFINITY, INFINITY, INFINITY }, mx[3] = { -INFINITY, -INFINITY, -INFINITY };
+    if (j < n) {
         const uint32_t p = idx_sorted[j];
         const float* t = tri_in + (size_t)p * 9;
         float v[9];
 #pragma unroll
         for (int i = 0; i < 9; i++) v[i] = __ldg(t + i);
-        float mn[3], mx[3];
+        const uint32_t last = (j + 1 == n || keys_sorted[j + 1] != keys_sorted[j]) ? 1u : 0u;
+        float4* dst = reinterpret_cast<float4*>(tris + j);
+        __stcs(dst, make_float4(v[0], v[1], v[2], __fsub_rn(v[3], v[0])));
+        __stcs(dst + 1, make_float4(__fsub_rn(v[4], v[1]), __fsub_rn(v[5], v[2]), __fsub_rn(v[6], v[0]), __fsub_rn(v[7], v[1])));
+        __stcs(dst + 2, make_float4(__fsub_rn(v[8], v[2]), __uint_as_float(p), __uint_as_float(last), __uint_as_float(j)));
         minmax3(v[0], v[3], v[6], mn[0], mx[0]);
         minmax3(v[1], v[4], v[7], mn[1], mx[1]);
         minmax3(v[2], v[5], v[8], mn[2], mx[2]);
-        if (j == s0) {
 #pragma unroll
-            for (int a = 0; a < 3; a++) { box.lo[a] = mn[a]; box.hi[a] = mx[a]; }
-        } else {
-#pragma unroll
-            for (int a = 0; a < 3; a++) { box.lo[a] = fminf(box.lo[a], mn[a]); box.hi[a] = fmaxf(box.hi[a], mx[a]); }
+        for (int a = 0; a < 3; a++) {
+            heaps[(size_t)a * 2 * P + P + j] = mx[a];
+            heaps[(size_t)(3 + a) * 2 * P + P + j] = mn[a];
         }
-        float4 q0 = make_float4(v[0], v[1], v[2], __fsub_rn(v[3], v[0]));
-        float4 q1 = make_float4(__fsub_rn(v[4], v[1]), __fsub_rn(v[5], v[2]), __fsub_rn(v[6], v[0]), __fsub_rn(v[7], v[1]));
-        float4 q2 = make_float4(__fsub_rn(v[8], v[2]), __uint_as_float(p), __uint_as_float(j + 1 == s1 ? 1u : 0u), __uint_as_float(j));
-        float4* dst = reinterpret_cast<float4*>(tris + j);
-        dst[0] = q0; dst[1] = q1; dst[2] = q2;
     }
-    if (nu < 2) return;
+#pragma unroll
+    for (int a = 0; a < 3; a++) { s[a][threadIdx.x] = mx[a]; s[3 + a][threadIdx.x] = mn[a]; }
+    heap_reduce_block(s, heaps, P, P);
+}
 
-    uint32_t left = k, right = k;
-    bool have_node = false;
-    float cl0 = 0.f, cl1 = 0.f;
-    uint32_t ref_l = 0, ref_r = 0;
-    for (;;) {
-        const bool is_root = (left == 0 && right == nu - 1);
-        bool am_left = false;
-        if (!is_root) {
-            if (left == 0) am_left = true;
-            else if (right == nu - 1) am_left = false;
-            else {
-                int dl = __clz(umc[left - 1] ^ umc[left]);
-                int dr = __clz(umc[right] ^ umc[right + 1]);
-                am_left = dr > dl;       // never equal for distinct sorted keys
-            }
-        }
-        if (have_node) {
-            uint32_t idx = is_root ? 0u : (am_left ? right : left);
-            BihNode nd; nd.clip0 = cl0; nd.clip1 = cl1; nd.ref_l = ref_l; nd.ref_r = ref_r;
-            *reinterpret_cast<float4*>(nodes + idx) = *reinterpret_cast<float4*>(&nd);
-        }
-        if (is_root) break;
-        const uint32_t ps = am_left ? right : left - 1;     // parent splits between leaves ps and ps+1
-        float4* mine = boxscratch + (size_t)ps * 4 + (am_left ? 0 : 2);
-        __stcg(mine, make_float4(box.lo[0], box.lo[1], box.lo[2], box.hi[0]));
-        __stcg(mine + 1, make_float4(box.hi[1], box.hi[2], 0.f, 0.f));
-        __threadfence();
-        const int other = atomicExch(&arrive[ps], (int)(am_left ? left : right));
-        if (other < 0) return;                               // first child to arrive leaves its box behind
-        __threadfence();
-        const float4* sib = boxscratch + (size_t)ps * 4 + (am_left ? 2 : 0);
-        float4 b0 = __ldcg(sib), b1 = __ldcg(sib + 1);
-        Box sb; sb.lo[0] = b0.x; sb.lo[1] = b0.y; sb.lo[2] = b0.z; sb.hi[0] = b0.w; sb.hi[1] = b1.x; sb.hi[2] = b1.y;
-        const Box& lbox = am_left ? box : sb;
-        const Box& rbox = am_left ? sb : box;
-        const uint32_t a = am_left ? left : (uint32_t)other;
-        const uint32_t b = am_left ? (uint32_t)other : right;
-        const int axis = (__clz(umc[ps] ^ umc[ps + 1]) + 1) % 3;    // R/src/CUDAKernels.cu:702-706
-        cl0 = pick(lbox.hi, axis);
-        cl1 = pick(rbox.lo, axis);
-        // a radix-tree node over leaves [l,r] splits on the first bit in which umc[l] and umc[r] differ,
-        // so a child's axis follows from its range ends (== (lcp(children of the child) + 1) % 3)
-        ref_l = (a == ps) ? BIH_REF_LEAFREF(first[ps]) : BIH_REF_NODE(ps, (__clz(umc[a] ^ umc[ps]) + 1) % 3);
-        ref_r = (ps + 1 == b) ? BIH_REF_LEAFREF(first[ps + 1]) : BIH_REF_NODE(ps + 1, (__clz(umc[ps + 1] ^ umc[b]) + 1) % 3);
-        if (a == 0 && b == nu - 1) hdr->root_axis = (uint32_t)axis;
-        Box u;
+// 8 more levels above the level of `in_count` used elements that starts at heap index `in_base`
+__global__ void __launch_bounds__(256) k_heap_up(float* __restrict__ heaps, uint32_t P, uint32_t in_base, uint32_t in_count) {
+    __shared__ float s[6][256];
+    const uint32_t i = blockIdx.x * 256u + threadIdx.x;
 #pragma unroll
-        for (int i = 0; i < 3; i++) { u.lo[i] = fminf(lbox.lo[i], rbox.lo[i]); u.hi[i] = fmaxf(lbox.hi[i], rbox.hi[i]); }
-        box = u;
-        left = a; right = b;
-        have_node = true;
+    for (int c = 0; c < 6; c++)
+        s[c][threadIdx.x] = i < in_count ? heaps[(size_t)c * 2 * P + in_base + i] : (c < 3 ? -INFINITY : INFINITY);
+    heap_reduce_block(s, heaps, P, in_base);
+}
+
+template <bool IS_MAX>
+__device__ __forceinline__ float heap_range(const float* __restrict__ h, uint32_t P, uint32_t l, uint32_t r /* inclusive */) {
+    float res = IS_MAX ? -INFINITY : INFINITY;
+    l += P; r += P + 1;
+    while (l < r) {
+        if (l & 1u) { const float x = __ldg(h + l); res = IS_MAX ? fmaxf(res, x) : fminf(res, x); l++; }
+        if (r & 1u) { r--; const float x = __ldg(h + r); res = IS_MAX ? fmaxf(res, x) : fminf(res, x); }
+        l >>= 1; r >>= 1;
     }
+    return res;
+}
+
+__global__ void __launch_bounds__(128) k_nodes(const uint32_t* __restrict__ umc, const uint32_t* __restrict__ first,
+                                               BihHeader* hdr, const float* __restrict__ heaps, uint32_t P,
+                                               BihNode* __restrict__ nodes) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nu = (int)hdr->nu;
+    if (idx > nu - 2) return;
+    const uint32_t cur = __ldg(umc + idx);
+    // common-prefix length with leaf j, -1 outside the array (R/src/CUDAKernels.cu:600-614,628-631)
+    auto lcp = [&](int j) -> int { return (j < 0 || j > nu - 1) ? -1 : __clz(cur ^ __ldg(umc + j)); };
+    const int d = lcp(idx + 1) > lcp(idx - 1) ? 1 : -1;          // :616 (never equal for distinct sorted keys)
+    const int lcp_min = lcp(idx - d);                            // :620
+    int l_max = 1;
+    do { l_max *= 2; } while (lcp(idx + l_max * d) > lcp_min);   // :624-633
+    int l = 0;
+    for (int t = l_max / 2; t >= 1; t /= 2)                      // :638-650
+        if (lcp(idx + (l + t) * d) > lcp_min) l += t;
+    const int other_end = idx + l * d;                           // :651
+    const int lcp_ends = lcp(other_end);                         // :652
+    int s = 0;
+    for (int t = l;;) {                                          // :658-675
+        t = (t + 1) >> 1;
+        if (lcp(idx + (s + t) * d) > lcp_ends) s += t;
+        if (t == 1) break;
+    }
+    const int split = idx + s * d + min(d, 0);                   // :677
+    const int a = min(idx, other_end), b = max(idx, other_end);
+    const uint32_t ms = __ldg(umc + split), ms1 = __ldg(umc + split + 1);
+    const int axis = (__clz(ms ^ ms1) + 1) % 3;                  // :702-706
+    // a node over leaves [l,r] splits on the first bit in which umc[l] and umc[r] differ, so a child's axis
+    // follows from its range ends; it is stored in the parent's reference (see bihrt_internal.cuh)
+    const uint32_t ref_l = (a == split) ? BIH_REF_LEAFREF(__ldg(first + split))
+                                        : BIH_REF_NODE(split, (__clz(__ldg(umc + a) ^ ms) + 1) % 3);
+    const uint32_t ref_r = (split + 1 == b) ? BIH_REF_LEAFREF(__ldg(first + split + 1))
+                                            : BIH_REF_NODE(split + 1, (__clz(ms1 ^ __ldg(umc + b)) + 1) % 3);
+    // leaves [a, split] are slots [first[a], first[split+1]); leaves [split+1, b] are [first[split+1], first[b+1])
+    const uint32_t sa = __ldg(first + a), sm = __ldg(first + split + 1), sb = __ldg(first + b + 1);
+    const float cl0 = heap_range<true>(heaps + (size_t)axis * 2 * P, P, sa, sm - 1);
+    const float cl1 = heap_range<false>(heaps + (size_t)(3 + axis) * 2 * P, P, sm, sb - 1);
+    *reinterpret_cast<float4*>(nodes + idx) = make_float4(cl0, cl1, __uint_as_float(ref_l), __uint_as_float(ref_r));
+    if (idx == 0) hdr->root_axis = (uint32_t)axis;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -467,12 +553,17 @@ int bihrt_build_launch(bihrt_ctx* c) {
     const size_t lb_words = (size_t)4 * os_tiles * 256 + rle_tiles;
     if (lb_words > c->lookback_words) return bihrt_fail(c, BIHRT_ERR_INTERNAL, "look-back buffer too small");
 
+    int pe = 0;
+#define PROF_MARK() do { if (c->opt_profile && pe < BIHRT_PROF_EVENTS) cudaEventRecord(c->prof_ev[pe++], st); } while (0)
+    PROF_MARK();
     k_init<<<1, 256, 0, st>>>(c->d_hist, c->d_scenebox_enc, c->d_hdr, n);
     BIHRT_CUDA(c, cudaMemsetAsync(c->d_lookback, 0, lb_words * 4, st));
-    BIHRT_CUDA(c, cudaMemsetAsync(c->d_arrive, 0xFF, (size_t)n * 4, st));
-    const int stream_grid = (int)min((uint32_t)(c->sm_count * 8), (n + 255) / 256);
+    PROF_MARK();   // 1: after init + memsets
+    const int stream_grid = (int)max(1u, min((uint32_t)(c->sm_count * 3), ((n >> 2) + 255) / 256));
     k_scene_box<<<stream_grid, 256, 0, st>>>(c->d_tri_in, n, c->d_scenebox_enc);
+    PROF_MARK();   // 2
     k_morton<<<stream_grid, 256, 0, st>>>(c->d_tri_in, n, c->d_scenebox_enc, c->d_keys[0], c->d_hist, c->d_hdr);
+    PROF_MARK();   // 3: after morton
     int cur = 0;
     for (int pass = 0; pass < 4; pass++) {
         uint32_t* lb = c->d_lookback + (size_t)pass * os_tiles * 256;
@@ -481,13 +572,30 @@ int bihrt_build_launch(bihrt_ctx* c) {
         else
             k_onesweep<false><<<os_tiles, OS_THREADS, 0, st>>>(c->d_keys[cur], c->d_vals[cur], c->d_keys[cur ^ 1], c->d_vals[cur ^ 1], n, pass, c->d_hist, lb, c->d_hdr);
         cur ^= 1;
+        PROF_MARK();   // 4..7: after each sort pass
     }
     // 4 passes: sorted data is back in buffer 0
-    k_rle<<<rle_tiles, 256, 0, st>>>(c->d_keys[cur], n, c->d_umc, c->d_first, c->d_hist,
-                                     c->d_lookback + (size_t)4 * os_tiles * 256, c->d_hdr);
-    k_tree<<<(n + 127) / 128, 128, 0, st>>>(c->d_tri_in, c->d_vals[cur], c->d_umc, c->d_first, c->d_hdr, c->d_nodes, c->d_tris,
-                                            c->d_arrive, reinterpret_cast<float4*>(c->d_boxscratch));
-    c->kernel_launches += 9;    // k_init, k_scene_box, k_morton, 4 x k_onesweep, k_rle, k_tree
+    uint32_t* tile_cnt = c->d_lookback + (size_t)4 * os_tiles * 256;
+    k_rle_count<<<rle_tiles, 256, 0, st>>>(c->d_keys[cur], n, tile_cnt);
+    k_rle_scan<<<1, 1024, 0, st>>>(tile_cnt, rle_tiles, n, c->d_first, c->d_hdr);
+    k_rle_write<<<rle_tiles, 256, 0, st>>>(c->d_keys[cur], n, tile_cnt, c->d_umc, c->d_first);
+    PROF_MARK();   // 8: after rle
+    // heaps are padded to a power of two >= n (Nu <= n is only known on the device)
+    uint32_t P = 256;
+    while (P < n) P <<= 1;
+    k_reorder<<<(n + 255) / 256, 256, 0, st>>>(c->d_tri_in, c->d_vals[cur], c->d_keys[cur], n, c->d_tris, c->d_heaps, P);
+    PROF_MARK();   // 9: after reorder + slot boxes
+    int launches = 0;
+    for (uint32_t lvl = P >> 8, used = (n + 255) / 256; lvl > 1; lvl >>= 8, used = (used + 255) / 256) {   // level with `lvl` elements
+        k_heap_up<<<(used + 255) / 256, 256, 0, st>>>(c->d_heaps, P, lvl, used);
+        launches++;
+    }
+    PROF_MARK();   // 10: after upper heap levels
+    k_nodes<<<(n + 127) / 128, 128, 0, st>>>(c->d_umc, c->d_first, c->d_hdr, c->d_heaps, P, c->d_nodes);
+    PROF_MARK();   // 11: after nodes
+    PROF_MARK();   // 12: after reorder
+    c->prof_count = pe;
+    c->kernel_launches += 12 + launches;   // k_init, k_scene_box, k_morton, 4 x k_onesweep, 3 x k_rle_*, k_reorder, k_heap_up.., k_nodes
     BIHRT_CUDA(c, cudaGetLastError());
     return BIHRT_OK;
 }
