@@ -115,7 +115,7 @@ int bihrt_create(bihrt_ctx** out, const bihrt_config* cfg) {
     rc |= dev_alloc(c, &c->d_hist, 2048);
     rc |= dev_alloc(c, &c->d_scenebox_enc, 8);
     rc |= dev_alloc(c, &c->d_counters, 8);
-    rc |= dev_alloc(c, &c->d_work, 4);
+    rc |= dev_alloc(c, &c->d_work, 1024);
     if (rc) { bihrt_destroy(c); return BIHRT_ERR_NOMEM; }
     *out = c;
     return BIHRT_OK;
@@ -162,6 +162,7 @@ int bihrt_set_option(bihrt_ctx* c, const char* name, int64_t v) {
         c->opt_profile = (int)v;
         if (v) for (int i = 0; i < BIHRT_PROF_EVENTS; i++) if (!c->prof_ev[i]) cudaEventCreate(&c->prof_ev[i]);
     }
+    else if (!strcmp(name, "trace_sm_queues")) c->opt_sm_queues = (int)v;
     else if (!strcmp(name, "trace_vote_wait")) c->opt_vote_wait = (int)v;
     else if (!strcmp(name, "trace_vote_walk")) c->opt_vote_walk = (int)v;
     else if (!strcmp(name, "trace_chunk_items")) c->opt_chunk_items = (int)std::max<int64_t>(32, (v + 31) / 32 * 32);
@@ -360,6 +361,7 @@ static void base_args(bihrt_ctx* c, TraceArgs& a) {
     a.shard_index = 0; a.shard_count = 1;
     a.refill_threshold = c->opt_refill_threshold; a.chunk_items = c->opt_chunk_items;
     a.vote_wait = c->opt_vote_wait; a.vote_walk = c->opt_vote_walk;
+    a.queues = c->opt_sm_queues;      // resolved per launch in bihrt_trace_launch (-1 = by ray count)
 }
 
 // outputs may individually be host or device; host ones are staged through d_io

@@ -106,6 +106,7 @@ struct bihrt_ctx {
     int opt_refill_threshold = 32;
     int opt_chunk_items = 32;
     int opt_vote_wait = 1, opt_vote_walk = 1;
+    int opt_sm_queues = -1; // 1: per-SM work queues (tile locality in L1), 0: one global counter, -1: by launch size
     int opt_sort_passes = 4;
     int64_t kernel_launches = 0;
     int opt_profile = 0;    // record an event after every build stage (bihrt_get_stat "build_stage_us_<i>")
@@ -130,7 +131,8 @@ struct TraceArgs {
     uint32_t* fb;
     unsigned long long* counters; uint32_t* work;
     int refill_threshold;   // lanes whose ray ended wait until this many are idle (or nobody is busy)
-    int chunk_items;        // work items (rays / pixels) a warp takes from the global counter at once
+    int chunk_items;        // work items (rays / pixels) a warp takes from the global counter at once (queues == 1)
+    int queues;             // > 1: one work queue per SM (tile t -> queue t % queues) with stealing
     int vote_wait, vote_walk;   // node phase also ends when waiters * vote_wait > walkers * vote_walk (0,x = never)
 };
 int bihrt_trace_launch(bihrt_ctx* c, const TraceArgs& a, int mode /*0 rays,1 render fb,2 render hits*/, bool counted);
