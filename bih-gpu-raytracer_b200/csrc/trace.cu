@@ -36,6 +36,39 @@
 
 struct Hit { float t; int slot; };
 
+template <bool COUNTED>
+__device__ __forceinline__ void test_leaf(const char* __restrict__ first_tri, float ox, float oy, float oz,
+                                          float dx, float dy, float dz, Hit& h, uint32_t& ntris) {
+    const float4* p = reinterpret_cast<const float4*>(first_tri);
+    for (;;) {
+        const float4 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2);
+        if (COUNTED) ntris++;
+        const float e1x = q0.w, e1y = q1.x, e1z = q1.y, e2x = q1.z, e2y = q1.w, e2z = q2.x;
+        // pvec = cross(dir, e2); det = dot(e1, pvec)                       R/src/CUDAKernels.cu:24-26
+        const float px = __fsub_rn(__fmul_rn(dy, e2z), __fmul_rn(e2y, dz));
+        const float py = __fsub_rn(__fmul_rn(dz, e2x), __fmul_rn(e2z, dx));
+        const float pz = __fsub_rn(__fmul_rn(dx, e2y), __fmul_rn(e2x, dy));
+        const float det = __fadd_rn(__fadd_rn(__fmul_rn(e1x, px), __fmul_rn(e1y, py)), __fmul_rn(e1z, pz));
+        if (!(det < DET_EPS)) {
+            const float inv = __frcp_rn(det);        // == (float)(1.0 / (double)det), :31 (53 >= 2*24+2 bits)
+            const float tx = __fsub_rn(ox, q0.x), ty = __fsub_rn(oy, q0.y), tz = __fsub_rn(oz, q0.z);
+            const float u = __fmul_rn(__fadd_rn(__fadd_rn(__fmul_rn(tx, px), __fmul_rn(ty, py)), __fmul_rn(tz, pz)), inv);
+            if (!(u < 0.f || u > 1.f)) {
+                const float qx = __fsub_rn(__fmul_rn(ty, e1z), __fmul_rn(e1y, tz));
+                const float qy = __fsub_rn(__fmul_rn(tz, e1x), __fmul_rn(e1z, tx));
+                const float qz = __fsub_rn(__fmul_rn(tx, e1y), __fmul_rn(e1x, ty));
+                const float v = __fmul_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, qx), __fmul_rn(dy, qy)), __fmul_rn(dz, qz)), inv);
+                if (!(v < 0.f || __fadd_rn(u, v) > 1.f)) {
+                    const float t = __fmul_rn(__fadd_rn(__fadd_rn(__fmul_rn(e2x, qx), __fmul_rn(e2y, qy)), __fmul_rn(e2z, qz)), inv);
+                    if (t > 0.f && t < h.t) { h.t = t; h.slot = (int)__float_as_uint(q2.w); }   // :218-221, slot = sorted index
+                }
+            }
+        }
+        if (__float_as_uint(q2.z) & 1u) break;      // last triangle of the leaf
+        p += 3;
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // MODE 0: ray list -> (t, slot, prim);  1: camera -> packed framebuffer;  2: camera -> per-sample hits
 // Work item = one ray (MODE 0) or one pixel with its spp samples (MODE 1/2).
