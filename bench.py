@@ -331,25 +331,73 @@ def run_ours(args, rank, world, local_rank):
         if roofline:
             out["roofline"] = roofline
 
-    # ---- N=1 extras: the other BASELINE sizes and the CPU baseline --------------------------------
+    # ---- N=1 extras: the other BASELINE configs / sizes and the baselines -------------------------
     if rank == 0 and world == 1 and not args.no_extras:
-        sizes = {}
-        for key in ("70k", "260k", "1m", "10m"):
-            try:
+        def med(fn, k=5):
+            fn(); r.sync()
+            return float(np.median([timed_loop(fn, 1) for _ in range(k)]))
+
+        def primary(c2, w, h, s_):
+            return w * h * s_ / (med(lambda: r.render(c2, w, h, spp=s_, jitter=s_ > 1)) * 1e-3) / 1e6
+
+        configs = {}
+        try:
+            # config 1: Cornell box, 512x512, 1 spp
+            r.load_models(torch.from_numpy(scenes.cornell_box()).to(dev)); r.build()
+            configs["config1_cornell_32tri_512x512_1spp"] = {"primary_mrays_s": primary(scenes.cornell_camera(), 512, 512, 1)}
+            # sizes: build ms/Mtri and 1080p primary rays on the displaced spheres of configs 2/4/5
+            c2 = scenes.pinhole_camera(aspect=1920 / 1080)
+            for key, label in (("70k", "config2_70k_1080p"), ("260k", "sphere_260k_1080p"), ("1m", "config5_1m_1080p"), ("10m", "config4_10m")):
                 t2 = scenes.displaced_sphere(scenes.SPHERE_NSEG[key])
                 d = torch.from_numpy(t2).to(dev)
-                r.load_models(d); r.build(); r.sync()
-                tb = [timed_loop(lambda: r.build(), 1) for _ in range(5)]
-                c2 = scenes.pinhole_camera(aspect=1920 / 1080)
-                r.render(c2, 1920, 1080, spp=4, jitter=True); r.sync()
-                tt = [timed_loop(lambda: r.render(c2, 1920, 1080, spp=4, jitter=True), 1) for _ in range(5)]
-                sizes[key] = {"triangles": len(t2), "build_ms_per_mtri": float(np.median(tb)) / (len(t2) / 1e6),
-                              "primary_mrays_s_1080p_4spp": 1920 * 1080 * 4 / (float(np.median(tt)) * 1e-3) / 1e6}
+                r.load_models(d)
+                bms = med(lambda: r.build())
+                e = {"triangles": len(t2), "leaves": r.build_info()["nu"], "build_ms": bms, "build_ms_per_mtri": bms / (len(t2) / 1e6),
+                     "primary_mrays_s_1080p_1spp": primary(c2, 1920, 1080, 1), "primary_mrays_s_1080p_4spp": primary(c2, 1920, 1080, 4)}
+                if key == "1m":      # config 5: animated frame = rebuild + trace, 1080p
+                    tms = med(lambda: r.render(c2, 1920, 1080, spp=1))
+                    fms = med(lambda: (r.build(), r.render(c2, 1920, 1080, spp=1)))
+                    e["animated_frame_1080p_1spp"] = {"build_ms": bms, "trace_ms": tms, "frame_ms": fms, "fps": 1e3 / fms}
+                if key == "10m":     # config 4: 4K x 16 spp
+                    c4 = scenes.pinhole_camera(aspect=3840 / 2160)
+                    e["primary_mrays_s_4k_16spp"] = 3840 * 2160 * 16 / (med(lambda: r.render(c4, 3840, 2160, spp=16, jitter=True), 3) * 1e-3) / 1e6
+                configs[label] = e
                 del d
-            except Exception as e:           # noqa
-                sizes[key] = {"error": str(e)[:100]}
-        out["sizes"] = sizes
+            # config 3: atrium, 1080p primary + shadow rays to a point light + one diffuse bounce (ray lists on the device)
+            ta = scenes.atrium()
+            r.load_models(torch.from_numpy(ta).to(dev))
+            bms = med(lambda: r.build())
+            ca = scenes.atrium_camera(1920 / 1080)
+            e = {"triangles": len(ta), "build_ms_per_mtri": bms / (len(ta) / 1e6), "primary_mrays_s_1080p_1spp": primary(ca, 1920, 1080, 1)}
+            t_, s_, p_ = r.render_hits(ca, 1920, 1080, spp=1)
+            org = np.broadcast_to(ca[:3], (len(t_), 3))
+            u = (np.arange(1920, dtype=np.float32) + 0.5) / 1920
+            v = (np.arange(1080, dtype=np.float32) + 0.5) / 1080
+            dirs = (ca[3:6][None, None, :] + u[None, :, None] * ca[6:9][None, None, :] + v[:, None, None] * ca[9:12][None, None, :] - ca[:3]).reshape(-1, 3)
+            hit = s_ >= 0
+            P = org[hit] + t_[hit, None] * dirs[hit]
+            vv = ta[p_[hit]].reshape(-1, 3, 3)
+            nrm = np.cross(vv[:, 1] - vv[:, 0], vv[:, 2] - vv[:, 0])
+            nrm /= np.maximum(np.linalg.norm(nrm, axis=1, keepdims=True), 1e-20)
+            P = (P + 1e-3 * nrm).astype(np.float32)
+            light = np.array([0.0, 0.8, 0.0], np.float32)
+            rng = np.random.default_rng(1984)
+            dd = rng.normal(size=P.shape)
+            dd /= np.linalg.norm(dd, axis=1, keepdims=True)
+            dd = np.where((dd * nrm).sum(1, keepdims=True) < 0, -dd, dd)
+            for nm, batch in (("shadow", np.concatenate([P, light - P], 1)), ("bounce", np.concatenate([P, dd], 1))):
+                db = torch.from_numpy(np.ascontiguousarray(batch, np.float32)).to(dev)
+                ot = torch.empty(len(batch), dtype=torch.float32, device=dev)
+                os_ = torch.empty(len(batch), dtype=torch.int32, device=dev)
+                ms_b = med(lambda: r.trace(db, t=ot, slot=os_, prim=os_))
+                e[nm + "_mrays_s"] = len(batch) / (ms_b * 1e-3) / 1e6
+                e[nm + "_rays"] = len(batch)
+            configs["config3_atrium_262k_1080p"] = e
+        except Exception as ex:           # noqa
+            configs["error"] = repr(ex)[:200]
+        out["configs"] = configs
         out["cpu_baseline"] = cpu_baseline(args, tri, cam)
+        out["reference_kernels_b200"] = reference_kernels_baseline(args, tri, cam)
     if rank == 0:
         emit(out)
     r.close()
@@ -377,6 +425,33 @@ def cpu_baseline(args, tri, cam):
                       "semantics, OpenMP %d threads" % (w, h, len(rays), cores),
             "pruned_traversal_mrays_s": len(rays) / dt_p / 1e6,
             "build_ms_per_mtri": build_s * 1e3 / (len(tri) / 1e6), "build_threads": 1}
+
+
+def reference_kernels_baseline(args, tri, cam):
+    """The reference's own BuildTree / FindClipPlanes / TraverseTree (+ the thrust calls of its Render),
+    compiled unmodified for sm_100a (oracle/_ref, built in the dev container), on this GPU: a reported
+    baseline next to the CPU one, 1 GPU only."""
+    try:
+        from oracle import oracle as O
+        from oracle import ref_harness
+        if not ref_harness.available():
+            return {"unavailable": "oracle/_ref/libref_harness.so not built (reference tree absent at build time)"}
+        ob = O.Bih(tri)
+        ref = ref_harness.RefScene(ob)
+        ref.build()
+        bms = []
+        for _ in range(5):
+            ref.build(); bms.append(ref.build_ms())
+        w, h = cpu_sample(args, 4)
+        rays = O.camera_rays(cam, w, h)
+        _, _, ms = ref.trace(rays, reps=3)
+        ref.close()
+        return {"build_ms_per_mtri": float(np.median(bms)) / (len(tri) / 1e6), "trace_mrays_s": len(rays) / (ms * 1e-3) / 1e6,
+                "sample": "%dx%d pixel-centre primary rays, reference TraverseTree kernel, 64-thread blocks; build = thrust transform/"
+                          "sequence/stable_sort_by_key/reduce_by_key/unique_by_key_copy + BuildTree + FindClipPlanes with the "
+                          "reference's cudaDeviceSynchronize after each step" % (w, h)}
+    except Exception as ex:           # noqa
+        return {"unavailable": repr(ex)[:200]}
 
 
 def main():
