@@ -105,7 +105,7 @@ struct bihrt_ctx {
     int opt_trace_variant = 0;
     int opt_refill_threshold = 32;
     int opt_chunk_items = 32;
-    int opt_vote_wait = 1, opt_vote_walk = 1;
+    int opt_vote_wait = 1, opt_vote_walk = 3;
     int opt_sm_queues = -1; // 1: per-SM work queues (tile locality in L1), 0: one global counter, -1: by launch size
     int opt_sort_passes = 4;
     int64_t kernel_launches = 0;
@@ -133,7 +133,8 @@ struct TraceArgs {
     int refill_threshold;   // lanes whose ray ended wait until this many are idle (or nobody is busy)
     int chunk_items;        // work items (rays / pixels) a warp takes from the global counter at once (queues == 1)
     int queues;             // > 1: one work queue per SM (tile t -> queue t % queues) with stealing
-    int vote_wait, vote_walk;   // node phase also ends when waiters * vote_wait > walkers * vote_walk (0,x = never)
+    int vote_wait, vote_walk;   // vote_wait != 0: the node phase also ends when the waiting lanes outnumber the walking ones;
+                                // vote_walk: node steps a lane may take between two votes
 };
 int bihrt_trace_launch(bihrt_ctx* c, const TraceArgs& a, int mode /*0 rays,1 render fb,2 render hits*/, bool counted);
 int bihrt_resolve_launch(bihrt_ctx* c, uint32_t* fb, int npix, int spp);

@@ -116,7 +116,9 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
     uint4 stack[STACK_DEPTH];
     int sp = 0;
     const uint32_t root_ref = BIH_REF_NODE(0, a.hdr->root_axis);
-    const int vote_wait = a.vote_wait, vote_walk = a.vote_walk;
+    const bool vote = a.vote_wait != 0;
+    const int steps_per_vote = a.vote_walk > 0 ? a.vote_walk : 1;
+    const uint32_t ray_smem = (uint32_t)__cvta_generic_to_shared(my_ray);
 
     for (;;) {
         // ================= refill: lanes whose ray has ended record it and get the next one ========
@@ -254,15 +256,21 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
 
         // ================= phase 1: internal nodes =====================================================
         // A lane steps through nodes until it holds a leaf, then waits.  The warp leaves the phase when
-        // nobody has a node left, or as soon as the waiting lanes outweigh the walking ones
-        // (waiters * vote_wait > walkers * vote_walk): finishing the node phase for a few stragglers
-        // with most lanes idle costs more than testing the held leaves first.
+        // nobody has a node left, or as soon as the waiting lanes outnumber the walking ones: finishing
+        // the node phase for a few stragglers with most lanes idle costs more than testing the held
+        // leaves first.
         for (;;) {
-            if ((int)cur >= 0) {
+#pragma unroll 1
+            for (int rep = 0; rep < steps_per_vote && (int)cur >= 0; rep++) {
                 bool popit = true;
                 if (pMin <= fminf(pMax, h.t)) {                        // entry check (closed interval)
-                    const float2 oi = my_ray[BIH_REF_AXIS(cur)];           // (origin, 1/dir) on this node's axis
-                    const float4 nd = __ldg(reinterpret_cast<const float4*>(nodes_b + (size_t)(cur & ~3u) * 4));
+                    // (origin, 1/dir) on this node's axis: one 64-bit LDS at ray_smem + axis * 8
+                    float2 oi;
+                    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(oi.x), "=f"(oi.y) : "r"(ray_smem + ((cur & 3u) << 3)));
+                    // node byte offset = (ref & ~3) * 4, as one 32x32->64 multiply-add on the base pointer
+                    const float4* np;
+                    asm("mad.wide.u32 %0, %1, 4, %2;" : "=l"(np) : "r"(cur & ~3u), "l"(nodes_b));
+                    const float4 nd = __ldg(np);
                     if (COUNTED) nnodes++;
                     const uint32_t rl = __float_as_uint(nd.z), rr = __float_as_uint(nd.w);
                     const bool neg = oi.y < 0.f;                           // near = sign[axis], :286
@@ -299,12 +307,18 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
             }
             const uint32_t m_walk = __ballot_sync(FULL, (int)cur >= 0);
             if (m_walk == 0) break;
-            const uint32_t m_wait = __ballot_sync(FULL, cur + 1u > 0x80000000u);      // a leaf (negative, not NONE)
-            if (__popc(m_wait) * vote_wait > __popc(m_walk) * vote_walk) break;
+            if (vote) {
+                const uint32_t m_wait = __ballot_sync(FULL, cur + 1u > 0x80000000u);  // a leaf (negative, not NONE)
+                if (__popc(m_wait) > __popc(m_walk)) break;
+            }
         }
         // ================= phase 2: the leaf this lane holds ===========================================
         if (cur + 1u > 0x80000000u) {
-            if (pMin <= fminf(pMax, h.t)) test_leaf<COUNTED>(tris_b + (size_t)(cur & 0x7FFFFFFCu) * 12, ox, oy, oz, dx, dy, dz, h, ntris);
+            if (pMin <= fminf(pMax, h.t)) {
+                const char* tp;
+                asm("mad.wide.u32 %0, %1, 12, %2;" : "=l"(tp) : "r"(cur & 0x7FFFFFFCu), "l"(tris_b));
+                test_leaf<COUNTED>(tp, ox, oy, oz, dx, dy, dz, h, ntris);
+            }
             if (sp > 0) {
                 sp--;
                 const uint4 e = stack[sp];

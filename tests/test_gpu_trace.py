@@ -175,7 +175,7 @@ def test_bih_blob_roundtrip(scenes, oracle):
 
 
 @pytest.mark.parametrize("opts", [
-    {"trace_vote_wait": 0}, {"trace_vote_wait": 1, "trace_vote_walk": 3}, {"trace_vote_wait": 4, "trace_vote_walk": 1},
+    {"trace_vote_wait": 0}, {"trace_vote_wait": 1, "trace_vote_walk": 1}, {"trace_vote_walk": 8}, {"trace_sm_queues": 1}, {"trace_sm_queues": 0},
     {"trace_refill_threshold": 4, "trace_chunk_items": 96},
     {"trace_refill_threshold": 1, "trace_vote_wait": 2, "trace_vote_walk": 1, "trace_blocks_per_sm": 3}])
 def test_scheduling_variants_do_not_change_results(renderer, scenes, oracle, opts):
