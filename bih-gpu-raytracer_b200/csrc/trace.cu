@@ -122,9 +122,14 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
 
     for (;;) {
         // ================= refill: lanes whose ray has ended record it and get the next one ========
+        // A lane whose ray ended moves on to the next SAMPLE of its own pixel as soon as `refill_threshold`
+        // lanes can (same pixel, so the warp stays coherent); new ITEMS are only handed out when the whole
+        // warp has drained (MODE 0 ray lists: items are single rays, so those are handed out at the
+        // threshold too).  Lanes that have nothing left park until then.
         const uint32_t idle = __ballot_sync(FULL, cur == NONE);
         const uint32_t busy = ~idle;
-        if (idle && (busy == 0 || __popc(idle) >= a.refill_threshold)) {
+        const uint32_t can = __ballot_sync(FULL, cur == NONE && (tracing || item != ~0ull || MODE == 0));
+        if (idle && (busy == 0 || __popc(can) >= a.refill_threshold)) {
             bool want_item = false;
             if (cur == NONE) {
                 if (tracing) {                                   // record the ray that just ended
@@ -155,6 +160,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
             }
             // hand out new items (warp-uniform control flow)
             uint32_t want = __ballot_sync(FULL, want_item);
+            if (MODE != 0 && busy != 0) want = 0;                 // pixels: wait for the whole warp
             while (want && !exhausted) {
                 if (pool_next >= pool_end) {
                     // Work comes in units of 32 items, grouped in tiles of 32 units (a 32x32-pixel tile / 1024
