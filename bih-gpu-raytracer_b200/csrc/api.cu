@@ -165,6 +165,7 @@ int bihrt_set_option(bihrt_ctx* c, const char* name, int64_t v) {
     else if (!strcmp(name, "trace_sm_queues")) c->opt_sm_queues = (int)v;
     else if (!strcmp(name, "trace_vote_wait")) c->opt_vote_wait = (int)v;
     else if (!strcmp(name, "trace_vote_walk")) c->opt_vote_walk = (int)v;
+    else if (!strcmp(name, "trace_refill_incoherent")) c->opt_refill_incoherent = (int)std::max<int64_t>(1, std::min<int64_t>(32, v));
     else if (!strcmp(name, "trace_chunk_items")) c->opt_chunk_items = (int)std::max<int64_t>(32, (v + 31) / 32 * 32);
     else return bihrt_fail(c, BIHRT_ERR_INVALID, "unknown option '%s'", name);
     return BIHRT_OK;
@@ -360,6 +361,7 @@ static void base_args(bihrt_ctx* c, TraceArgs& a) {
     a.counters = c->d_counters; a.work = c->d_work;
     a.shard_index = 0; a.shard_count = 1;
     a.refill_threshold = c->opt_refill_threshold; a.chunk_items = c->opt_chunk_items;
+    a.refill_incoherent = c->opt_refill_incoherent;
     a.vote_wait = c->opt_vote_wait; a.vote_walk = c->opt_vote_walk;
     a.queues = c->opt_sm_queues;      // resolved per launch in bihrt_trace_launch (-1 = by ray count)
 }

@@ -104,6 +104,7 @@ struct bihrt_ctx {
     int opt_trace_blocks_per_sm = 0;   // 0 = occupancy query
     int opt_trace_variant = 0;
     int opt_refill_threshold = 32;
+    int opt_refill_incoherent = 8;
     int opt_chunk_items = 32;
     int opt_vote_wait = 1, opt_vote_walk = 3;
     int opt_sm_queues = -1; // 1: per-SM work queues (tile locality in L1), 0: one global counter, -1: by launch size
@@ -131,6 +132,7 @@ struct TraceArgs {
     uint32_t* fb;
     unsigned long long* counters; uint32_t* work;
     int refill_threshold;   // lanes whose ray ended wait until this many are idle (or nobody is busy)
+    int refill_incoherent;  // threshold used instead for ray-list packets with mixed direction signs
     int chunk_items;        // work items (rays / pixels) a warp takes from the global counter at once (queues == 1)
     int queues;             // > 1: one work queue per SM (tile t -> queue t % queues) with stealing
     int vote_wait, vote_walk;   // vote_wait != 0: the node phase also ends when the waiting lanes outnumber the walking ones;

@@ -117,6 +117,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
     int sp = 0;
     const uint32_t root_ref = BIH_REF_NODE(0, a.hdr->root_axis);
     const bool vote = a.vote_wait != 0;
+    int thresh = a.refill_threshold;          // lanes that must be idle before a partial refill (warp-uniform)
     const int steps_per_vote = a.vote_walk > 0 ? a.vote_walk : 1;
     const uint32_t ray_smem = (uint32_t)__cvta_generic_to_shared(my_ray);
 
@@ -129,7 +130,9 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
         const uint32_t idle = __ballot_sync(FULL, cur == NONE);
         const uint32_t busy = ~idle;
         const uint32_t can = __ballot_sync(FULL, cur == NONE && (tracing || item != ~0ull || MODE == 0));
-        if (idle && (busy == 0 || __popc(can) >= a.refill_threshold)) {
+        if (idle && (busy == 0 || __popc(can) >= thresh)) {
+            const bool fresh = (busy == 0);          // the warp starts a new packet together
+            int new_thresh = -1;
             bool want_item = false;
             if (cur == NONE) {
                 if (tracing) {                                   // record the ray that just ended
@@ -232,6 +235,15 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
                 }
                 // Ray::Ray, R/src/Ray.cu:3-10
                 const float ix = __frcp_rn(dx), iy = __frcp_rn(dy), iz = __frcp_rn(dz);
+                if (MODE == 0 && fresh) {
+                    // ray lists: a packet whose directions disagree in sign is incoherent (diffuse bounces);
+                    // there, lanes that finish early are worth refilling before the whole packet has drained
+                    const uint32_t m = __activemask();
+                    const uint32_t bx = __ballot_sync(m, ix < 0.f), by = __ballot_sync(m, iy < 0.f), bz = __ballot_sync(m, iz < 0.f);
+                    // (one mixed axis is common in coherent packets that straddle a sign boundary; two are not)
+                    const bool mixed = ((bx != 0 && bx != m) + (by != 0 && by != m) + (bz != 0 && bz != m)) >= 2;
+                    new_thresh = mixed ? min(a.refill_threshold, a.refill_incoherent) : a.refill_threshold;
+                }
                 my_ray[0] = make_float2(ox, ix); my_ray[1] = make_float2(oy, iy); my_ray[2] = make_float2(oz, iz);
                 h.t = FLT_MAX; h.slot = -1; sp = 0; tracing = true;
                 // slab test against the scene box, R/src/CUDAKernels.cu:237-262 (same operation order)
@@ -255,6 +267,10 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
                     if (nu == 1) { cur = BIH_REF_LEAFREF(0); pMin = -FLT_MAX; pMax = FLT_MAX; }
                     else cur = root_ref;
                 }
+            }
+            if (MODE == 0) {
+                const uint32_t upd = __ballot_sync(FULL, new_thresh >= 0);
+                if (upd) thresh = __shfl_sync(FULL, new_thresh, __ffs(upd) - 1);
             }
             if (__ballot_sync(FULL, cur != NONE || tracing) == 0 && exhausted &&
                 __ballot_sync(FULL, item != ~0ull) == 0) break;
