@@ -369,29 +369,16 @@ def run_ours(args, rank, world, local_rank):
             bms = med(lambda: r.build())
             ca = scenes.atrium_camera(1920 / 1080)
             e = {"triangles": len(ta), "build_ms_per_mtri": bms / (len(ta) / 1e6), "primary_mrays_s_1080p_1spp": primary(ca, 1920, 1080, 1)}
-            t_, s_, p_ = r.render_hits(ca, 1920, 1080, spp=1)
-            org = np.broadcast_to(ca[:3], (len(t_), 3))
-            u = (np.arange(1920, dtype=np.float32) + 0.5) / 1920
-            v = (np.arange(1080, dtype=np.float32) + 0.5) / 1080
-            dirs = (ca[3:6][None, None, :] + u[None, :, None] * ca[6:9][None, None, :] + v[:, None, None] * ca[9:12][None, None, :] - ca[:3]).reshape(-1, 3)
-            hit = s_ >= 0
-            P = org[hit] + t_[hit, None] * dirs[hit]
-            vv = ta[p_[hit]].reshape(-1, 3, 3)
-            nrm = np.cross(vv[:, 1] - vv[:, 0], vv[:, 2] - vv[:, 0])
-            nrm /= np.maximum(np.linalg.norm(nrm, axis=1, keepdims=True), 1e-20)
-            P = (P + 1e-3 * nrm).astype(np.float32)
-            light = np.array([0.0, 0.8, 0.0], np.float32)
-            rng = np.random.default_rng(1984)
-            dd = rng.normal(size=P.shape)
-            dd /= np.linalg.norm(dd, axis=1, keepdims=True)
-            dd = np.where((dd * nrm).sum(1, keepdims=True) < 0, -dd, dd)
-            for nm, batch in (("shadow", np.concatenate([P, light - P], 1)), ("bounce", np.concatenate([P, dd], 1))):
-                db = torch.from_numpy(np.ascontiguousarray(batch, np.float32)).to(dev)
-                ot = torch.empty(len(batch), dtype=torch.float32, device=dev)
-                os_ = torch.empty(len(batch), dtype=torch.int32, device=dev)
+            # shadow rays to a point light and one cosine-weighted bounce, generated on the device from the
+            # primary hits (bihrt_secondary_rays), traced as ray lists
+            for nm, kind in (("shadow", "shadow"), ("bounce", "diffuse")):
+                db, _src = r.secondary_rays(ca, 1920, 1080, spp=1, kind=kind, light=(0.0, 0.8, 0.0))
+                ot = torch.empty(len(db), dtype=torch.float32, device=dev)
+                os_ = torch.empty(len(db), dtype=torch.int32, device=dev)
                 ms_b = med(lambda: r.trace(db, t=ot, slot=os_, prim=os_))
-                e[nm + "_mrays_s"] = len(batch) / (ms_b * 1e-3) / 1e6
-                e[nm + "_rays"] = len(batch)
+                e[nm + "_mrays_s"] = len(db) / (ms_b * 1e-3) / 1e6
+                e[nm + "_rays"] = len(db)
+                e[nm + "_generation_ms"] = med(lambda: r.secondary_rays(ca, 1920, 1080, spp=1, kind=kind, light=(0.0, 0.8, 0.0)), 3)
             configs["config3_atrium_262k_1080p"] = e
         except Exception as ex:           # noqa
             configs["error"] = repr(ex)[:200]

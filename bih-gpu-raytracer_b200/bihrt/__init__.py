@@ -65,7 +65,7 @@ ABI_SYMBOLS = [
     "bihrt_version", "bihrt_create", "bihrt_destroy", "bihrt_last_error", "bihrt_set_stream", "bihrt_sync",
     "bihrt_set_option", "bihrt_get_stat", "bihrt_scene_load_triangles", "bihrt_scene_update_vertices", "bihrt_scene_load_obj",
     "bihrt_build", "bihrt_get_build_info", "bihrt_export_reference_view", "bihrt_trace", "bihrt_trace_counted",
-    "bihrt_render", "bihrt_render_counted", "bihrt_render_shard", "bihrt_render_samples", "bihrt_framebuffer_resolve", "bihrt_render_hits", "bihrt_framebuffer", "bihrt_framebuffer_read",
+    "bihrt_render", "bihrt_render_counted", "bihrt_render_shard", "bihrt_render_samples", "bihrt_framebuffer_resolve", "bihrt_render_hits", "bihrt_secondary_rays", "bihrt_framebuffer", "bihrt_framebuffer_read",
     "bihrt_bih_blob_bytes", "bihrt_bih_export", "bihrt_bih_import",
 ]
 
@@ -268,6 +268,22 @@ class Renderer:
                                                 C.c_uint64(seed), C.c_uint32(RENDER_JITTER if jitter else 0),
                                                 _ptr(t), _ptr(slot), _ptr(prim)))
         return t, slot, prim
+
+    def secondary_rays(self, camera, w, h, spp=1, kind="shadow", light=(0.0, 0.0, 0.0), seed=1984, jitter=False):
+        """Device-side shadow / diffuse-bounce rays from the primary hits of a camera frame.
+        Returns (rays (M,6) float32 CUDA tensor, sample index (M,) int32 CUDA tensor)."""
+        import torch
+        cam = camera if isinstance(camera, Camera) else Camera.from_array(camera)
+        n = w * h * spp
+        dev = "cuda:%d" % self.device
+        rays = torch.empty((n, 6), dtype=torch.float32, device=dev)
+        src = torch.empty(n, dtype=torch.int32, device=dev)
+        cnt = C.c_int64()
+        lt = (C.c_float * 3)(*[float(x) for x in light])
+        self._check(self._lib.bihrt_secondary_rays(self._ctx, C.byref(cam), C.c_int32(w), C.c_int32(h), C.c_int32(spp), C.c_uint64(seed),
+                                                   C.c_uint32(RENDER_JITTER if jitter else 0), C.c_int32({"shadow": 0, "diffuse": 1}[kind]),
+                                                   lt, _ptr(rays), _ptr(src), C.byref(cnt)))
+        return rays[:cnt.value], src[:cnt.value]
 
     # -- m_cudaDestResource ---------------------------------------------------------------------------
     def framebuffer_ptr(self):

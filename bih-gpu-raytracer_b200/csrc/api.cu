@@ -508,6 +508,37 @@ int bihrt_render_hits(bihrt_ctx* c, const bihrt_camera* cam, int32_t w, int32_t 
     return unstage_outputs(c, n, o);
 }
 
+// ---- secondary rays ------------------------------------------------------------------------------
+int bihrt_secondary_rays(bihrt_ctx* c, const bihrt_camera* cam, int32_t w, int32_t h, int32_t spp, uint64_t seed, uint32_t flags,
+                         int32_t kind, const float light[3], bihrt_ray* out_rays, int32_t* out_sample, int64_t* count) {
+    ENTER(c);
+    int rc = render_check(c, cam, w, h, spp, 0, 1);
+    if (rc) return rc;
+    if (!out_rays || !count || !is_device_ptr(out_rays) || (out_sample && !is_device_ptr(out_sample)))
+        return bihrt_fail(c, BIHRT_ERR_INVALID, "out_rays / out_sample must be device buffers, count a host pointer");
+    if (kind != BIHRT_SECONDARY_SHADOW && kind != BIHRT_SECONDARY_DIFFUSE) return bihrt_fail(c, BIHRT_ERR_INVALID, "bad kind %d", kind);
+    static const float zero3[3] = { 0.f, 0.f, 0.f };
+    if (!light) light = zero3;
+    const int64_t n = (int64_t)w * h * spp;
+    const size_t ntiles = (size_t)((n + 255) / 256);
+    // staging: t[n] | slot[n] | tile counts
+    if ((rc = ensure_io(c, (size_t)n * 8 + ntiles * 4 + 512))) return rc;
+    float* d_t = (float*)c->d_io;
+    int32_t* d_slot = (int32_t*)((uint8_t*)c->d_io + (size_t)n * 4);
+    uint32_t* d_cnt = (uint32_t*)((uint8_t*)c->d_io + (size_t)n * 8);
+    TraceArgs a; base_args(c, a);
+    a.cam = *cam; a.w = w; a.h = h; a.spp = spp; a.seed = seed; a.flags = flags;
+    a.s_begin = 0; a.s_end = spp;
+    a.out_t = d_t; a.out_slot = d_slot; a.out_prim = nullptr;
+    if ((rc = bihrt_trace_launch(c, a, 2, false))) return rc;
+    if ((rc = bihrt_secondary_launch(c, d_t, d_slot, n, d_cnt, c->d_counters + 3, *cam, w, h, spp, seed, flags, kind, light, out_rays, out_sample))) return rc;
+    unsigned long long total = 0;
+    BIHRT_CUDA(c, cudaMemcpyAsync(&total, c->d_counters + 3, 8, cudaMemcpyDeviceToHost, c->stream));
+    BIHRT_CUDA(c, cudaStreamSynchronize(c->stream));
+    *count = (int64_t)total;
+    return BIHRT_OK;
+}
+
 // ---- framebuffer -------------------------------------------------------------------------------
 int bihrt_framebuffer(bihrt_ctx* c, uint32_t** dev_ptr, int32_t* w, int32_t* h) {
     if (!c) return BIHRT_ERR_INVALID;

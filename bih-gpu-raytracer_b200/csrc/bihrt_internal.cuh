@@ -140,6 +140,10 @@ struct TraceArgs {
 };
 int bihrt_trace_launch(bihrt_ctx* c, const TraceArgs& a, int mode /*0 rays,1 render fb,2 render hits*/, bool counted);
 int bihrt_resolve_launch(bihrt_ctx* c, uint32_t* fb, int npix, int spp);
+// shade.cu
+int bihrt_secondary_launch(bihrt_ctx* c, const float* t, const int32_t* slot, int64_t n, uint32_t* tile_cnt, unsigned long long* total,
+                           const bihrt_camera& cam, int w, int h, int spp, uint64_t seed, uint32_t flags, int kind, const float light[3],
+                           bihrt_ray* out_rays, int32_t* out_sample);
 
 // -------------------------------------------------------------------------------------------
 // device helpers

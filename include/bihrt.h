@@ -161,6 +161,19 @@ BIHRT_API int bihrt_framebuffer_resolve(bihrt_ctx* ctx, int32_t spp);   /* count
 BIHRT_API int bihrt_render_hits(bihrt_ctx* ctx, const bihrt_camera* cam, int32_t w, int32_t h, int32_t spp,
                       uint64_t seed, uint32_t flags, float* t, int32_t* slot, int32_t* prim);
 
+/* ---- secondary rays (the stage after the path; the reference's Color() is a stub, R/src/CUDAKernels.cu:370-389).
+ *      From the primary hits of a camera frame (the w*h*spp samples bihrt_render traces) build the next ray
+ *      batch ON THE DEVICE: every sample that hits emits one ray from the hit point (moved 1e-3 along the
+ *      geometric normal) to `light` (SHADOW; direction = light - origin, so t = 1 at the light) or in a
+ *      cosine-weighted direction about the normal (DIFFUSE; counter-based hash of seed, pixel, sample).  Rays
+ *      are written compacted and in sample order to out_rays (DEVICE, capacity w*h*spp); out_sample[i] (device,
+ *      may be NULL) = source sample.  *count (host) receives the number of rays.  Synchronises. */
+#define BIHRT_SECONDARY_SHADOW  0
+#define BIHRT_SECONDARY_DIFFUSE 1
+BIHRT_API int bihrt_secondary_rays(bihrt_ctx* ctx, const bihrt_camera* cam, int32_t w, int32_t h, int32_t spp, uint64_t seed,
+                         uint32_t flags, int32_t kind, const float light[3], bihrt_ray* out_rays, int32_t* out_sample,
+                         int64_t* count);
+
 /* ---- framebuffer: Renderer::m_cudaDestResource, R/src/Renderer.h:46, R/src/Renderer.cpp:762-768 */
 BIHRT_API int bihrt_framebuffer(bihrt_ctx* ctx, uint32_t** dev_ptr, int32_t* w, int32_t* h);  /* device pointer, owned by ctx */
 BIHRT_API int bihrt_framebuffer_read(bihrt_ctx* ctx, uint32_t* host_dst);                      /* synchronises */
