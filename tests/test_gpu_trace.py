@@ -197,3 +197,52 @@ def test_scheduling_variants_do_not_change_results(renderer, scenes, oracle, opt
         tt, ss, pp = renderer.render_hits(cam, w, h, spp=2, jitter=True)
         np.testing.assert_array_equal(ss, s1)
         np.testing.assert_array_equal(tt, t1)
+
+
+def test_axis_parallel_and_degenerate_rays(renderer, scenes, oracle):
+    """Rays with zero direction components (1/0 = inf, 0*inf = NaN plane distances), origins inside the scene,
+    on the scene box, and pointing away: the kernel must follow the oracle's IEEE behaviour exactly."""
+    tri = np.concatenate([scenes.cornell_box(), scenes.displaced_sphere(24) * 0.3])
+    ob = oracle.Bih(tri)
+    renderer.load_models(tri).build()
+    rng = np.random.default_rng(7)
+    n = 20000
+    o = rng.uniform(-1.2, 1.2, (n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    which = rng.integers(0, 7, n)
+    d[which == 0, 0] = 0.0                       # parallel to the yz plane
+    d[which == 1, 1] = 0.0
+    d[which == 2, 2] = 0.0
+    d[which == 3, :2] = 0.0                      # axis-parallel
+    o[which == 4] = np.round(o[which == 4] * 4) / 4      # origins on grid planes (walls at +-1, box faces)
+    d[which == 5] = np.sign(d[which == 5])       # diagonal directions
+    o[which == 6, 0] = -1.0                      # exactly on the scene box
+    d[(which == 3) & (d[:, 2] == 0), 2] = 1.0
+    rays = np.concatenate([o, d], 1).astype(np.float32)
+    t, s, p = renderer.trace(rays)
+    t0, s0, p0 = ob.trace(rays, "ref")
+    bad = s != s0
+    assert bad.sum() <= ID_MISMATCH_MAX * n, "%d of %d ids differ" % (bad.sum(), n)
+    np.testing.assert_array_equal(t[~bad], t0[~bad])
+    t1, s1, _ = ob.trace(rays, "proper")
+    np.testing.assert_array_equal(s, s1)         # the same logical algorithm, NaN handling included
+    np.testing.assert_array_equal(t, t1)
+
+
+def test_ten_million_triangles(renderer, scenes, oracle):
+    """BASELINE config 4 size (9 999 392 triangles): build compared with the oracle bit for bit (sorted codes,
+    permutation, leaves, every node) and a ray sample compared with the oracle's literal traversal."""
+    from conftest import assert_view_equals_oracle
+    tri = scenes.displaced_sphere(2236)
+    assert len(tri) == 9999392
+    renderer.load_models(tri).build()
+    v = renderer.reference_view()
+    codes = v["morton_codes"]
+    assert np.all(codes[1:] >= codes[:-1])
+    assert np.array_equal(np.sort(v["tris_indexes"]), np.arange(len(tri), dtype=np.uint32))
+    ob = oracle.Bih(tri)
+    assert_view_equals_oracle(v, ob)
+    rays = oracle.camera_rays(scenes.pinhole_camera(), 384, 216)
+    t, s, p = renderer.trace(rays)
+    t0, s0, p0 = ob.trace(rays, "ref")
+    compare(t, s, p, t0, s0, p0)
