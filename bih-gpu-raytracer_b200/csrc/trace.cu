@@ -26,7 +26,9 @@
 #define FULL 0xffffffffu
 #define STACK_DEPTH 32          // <= 31 items: one per Morton bit on a root-to-leaf path, plus one
 #define NONE 0xFFFFFFFFu        // "no item": leaf bit set, never a valid slot
+#ifndef TRACE_THREADS
 #define TRACE_THREADS 128
+#endif
 #ifndef TRACE_MIN_BLOCKS
 #define TRACE_MIN_BLOCKS 8        // <= 64 registers per thread
 #endif
