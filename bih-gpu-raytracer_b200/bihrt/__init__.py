@@ -64,7 +64,7 @@ class BuildInfo(C.Structure):
 ABI_SYMBOLS = [
     "bihrt_version", "bihrt_create", "bihrt_destroy", "bihrt_last_error", "bihrt_set_stream", "bihrt_sync",
     "bihrt_set_option", "bihrt_get_stat", "bihrt_scene_load_triangles", "bihrt_scene_update_vertices", "bihrt_scene_load_obj",
-    "bihrt_build", "bihrt_get_build_info", "bihrt_export_reference_view", "bihrt_trace", "bihrt_trace_counted",
+    "bihrt_build", "bihrt_refit", "bihrt_get_build_info", "bihrt_export_reference_view", "bihrt_trace", "bihrt_trace_counted",
     "bihrt_render", "bihrt_render_counted", "bihrt_render_shard", "bihrt_render_samples", "bihrt_framebuffer_resolve", "bihrt_render_hits", "bihrt_secondary_rays", "bihrt_framebuffer", "bihrt_framebuffer_read",
     "bihrt_bih_blob_bytes", "bihrt_bih_export", "bihrt_bih_import",
 ]
@@ -178,6 +178,11 @@ class Renderer:
     # -- first half of Renderer::Render -----------------------------------------------------------
     def build(self):
         self._check(self._lib.bihrt_build(self._ctx))
+        return self
+
+    def refit(self):
+        """Non-parity fast update after update_vertices: same topology, new clip planes (bihrt_refit)."""
+        self._check(self._lib.bihrt_refit(self._ctx))
         return self
 
     def build_info(self):

@@ -202,7 +202,7 @@ int bihrt_scene_load_triangles(bihrt_ctx* c, const float* xyz9, int64_t n) {
     if (n >= BIH_MAX_TRIS) return bihrt_fail(c, BIHRT_ERR_INVALID, "at most 2^29-1 triangles (29-bit child references)");
     int rc = ensure_capacity(c, n, true);
     if (rc) return rc;
-    c->n = n; c->have_scene = true; c->built = false;
+    c->n = n; c->have_scene = true; c->built = false; c->topology_valid = false;
     return upload_triangles(c, xyz9, n);
 }
 
@@ -270,6 +270,18 @@ int bihrt_build(bihrt_ctx* c) {
         int rc = bihrt_build_launch(c);
         if (rc) return rc;
     }
+    BIHRT_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+    c->built = true; c->build_timed = true; c->topology_valid = c->n > 0;
+    return BIHRT_OK;
+}
+
+int bihrt_refit(bihrt_ctx* c) {
+    ENTER(c);
+    if (!c->have_scene || !c->d_tri_in) return bihrt_fail(c, BIHRT_ERR_STATE, "no scene loaded");
+    if (!c->topology_valid) return bihrt_fail(c, BIHRT_ERR_STATE, "refit needs a full bihrt_build of the same triangle count first");
+    BIHRT_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+    int rc = bihrt_refit_launch(c);
+    if (rc) return rc;
     BIHRT_CUDA(c, cudaEventRecord(c->ev1, c->stream));
     c->built = true; c->build_timed = true;
     return BIHRT_OK;
@@ -601,7 +613,7 @@ int bihrt_bih_import(bihrt_ctx* c, const void* dev_src, uint64_t bytes) {
     BIHRT_CUDA(c, cudaMemcpyAsync(c->d_hdr, s, 64, cudaMemcpyDeviceToDevice, c->stream));
     if (nb) BIHRT_CUDA(c, cudaMemcpyAsync(c->d_nodes, s + 64, nb, cudaMemcpyDeviceToDevice, c->stream));
     if (tb) BIHRT_CUDA(c, cudaMemcpyAsync(c->d_tris, s + 64 + nb, tb, cudaMemcpyDeviceToDevice, c->stream));
-    c->n = h.n; c->built = true; c->build_timed = false;
+    c->n = h.n; c->built = true; c->build_timed = false; c->topology_valid = false;
     return BIHRT_OK;
 }
 

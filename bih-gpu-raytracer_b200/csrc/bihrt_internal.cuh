@@ -72,6 +72,7 @@ struct bihrt_ctx {
     float*   d_tri_in = nullptr;     // n x 9 floats (reference Triangle layout, 36 B)
     int64_t  n = 0, cap_n = 0;
     bool     have_scene = false, built = false;
+    bool     topology_valid = false;   // a full build on this context produced keys / order / leaves for the current n
 
     // BIH blob: [BihHeader | nodes (nu-1, padded) | tris (n)]  -- one allocation, one broadcast
     uint8_t* d_blob = nullptr;
@@ -121,6 +122,7 @@ int  bihrt_fail(bihrt_ctx* c, int code, const char* fmt, ...);
 
 // build.cu
 int bihrt_build_launch(bihrt_ctx* c);
+int bihrt_refit_launch(bihrt_ctx* c);
 // trace.cu
 struct TraceArgs {
     const BihHeader* hdr; const BihNode* nodes; const BihTri* tris;

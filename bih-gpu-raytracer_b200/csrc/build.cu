@@ -599,3 +599,38 @@ int bihrt_build_launch(bihrt_ctx* c) {
     BIHRT_CUDA(c, cudaGetLastError());
     return BIHRT_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// Refit (NOT a parity path): after bihrt_scene_update_vertices, keep the Morton order,
+// the leaves and the tree topology of the last full build and recompute only what depends on vertex
+// positions: scene box, leaf-ordered triangle records, AABB heaps, clip planes.  The result is a valid BIH
+// (every plane still bounds its subtree) but not the tree the reference would build for the moved vertices;
+// it is the cheap path for small deformations between full rebuilds (4 kernels instead of 12).
+// ------------------------------------------------------------------------------------------
+__global__ void k_refit_box(const uint32_t* __restrict__ enc, BihHeader* hdr) {
+    if (threadIdx.x < 3) { hdr->lo[threadIdx.x] = dec_float(enc[threadIdx.x]); hdr->hi[threadIdx.x] = dec_float(enc[3 + threadIdx.x]); }
+}
+__global__ void k_refit_init(uint32_t* enc) {
+    if (threadIdx.x < 3) { enc[threadIdx.x] = 0xFFFFFFFFu; enc[3 + threadIdx.x] = 0u; }
+}
+
+int bihrt_refit_launch(bihrt_ctx* c) {
+    const uint32_t n = (uint32_t)c->n;
+    cudaStream_t st = c->stream;
+    uint32_t P = 256;
+    while (P < n) P <<= 1;
+    const int stream_grid = (int)max(1u, min((uint32_t)(c->sm_count * 3), ((n >> 2) + 255) / 256));
+    k_refit_init<<<1, 32, 0, st>>>(c->d_scenebox_enc);
+    k_scene_box<<<stream_grid, 256, 0, st>>>(c->d_tri_in, n, c->d_scenebox_enc);
+    k_refit_box<<<1, 32, 0, st>>>(c->d_scenebox_enc, c->d_hdr);
+    k_reorder<<<(n + 255) / 256, 256, 0, st>>>(c->d_tri_in, c->d_vals[0], c->d_keys[0], n, c->d_tris, c->d_heaps, P);
+    int launches = 0;
+    for (uint32_t lvl = P >> 8, used = (n + 255) / 256; lvl > 1; lvl >>= 8, used = (used + 255) / 256) {
+        k_heap_up<<<(used + 255) / 256, 256, 0, st>>>(c->d_heaps, P, lvl, used);
+        launches++;
+    }
+    k_nodes<<<(n + 127) / 128, 128, 0, st>>>(c->d_umc, c->d_first, c->d_hdr, c->d_heaps, P, c->d_nodes);
+    c->kernel_launches += 5 + launches;
+    BIHRT_CUDA(c, cudaGetLastError());
+    return BIHRT_OK;
+}

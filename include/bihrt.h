@@ -121,6 +121,10 @@ BIHRT_API int bihrt_scene_load_obj(bihrt_ctx* ctx, const char* path);          /
 /* ---- build: first half of Renderer::Render (Morton transform, sort, RLE, Launch_BuildTree,
  *      Launch_FindClipPlanes), R/src/Renderer.cpp:422-503.  No host sync inside. ------------------ */
 BIHRT_API int bihrt_build(bihrt_ctx* ctx);
+/* NOT a parity path: after bihrt_scene_update_vertices keep the order, leaves and topology of the
+ * last full build and recompute scene box, triangle records and clip planes only (about half the time of a build).
+ * The BIH stays valid (planes bound their subtrees) but is not the tree the reference would build for the moved vertices. */
+BIHRT_API int bihrt_refit(bihrt_ctx* ctx);
 BIHRT_API int bihrt_get_build_info(bihrt_ctx* ctx, bihrt_build_info* out);     /* synchronises */
 BIHRT_API int bihrt_export_reference_view(bihrt_ctx* ctx, bihrt_refview* view); /* synchronises; see bihrt_refview */
 

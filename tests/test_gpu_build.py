@@ -116,3 +116,28 @@ def test_error_codes(renderer):
     with pytest.raises(bihrt.BihrtError) as e:
         renderer.load_models("/nonexistent/file.obj")
     assert e.value.code == -5
+
+
+def test_refit_keeps_hits_correct(renderer, scenes, oracle):
+    """bihrt_refit (non-parity fast path for animation): topology of the last build, new clip planes.  The
+    BIH must stay valid: hits on the moved mesh equal brute force over the moved triangles."""
+    import bihrt
+    a, b = scenes.displaced_sphere(96, phase=0.0), scenes.displaced_sphere(96, phase=0.15)
+    with pytest.raises(bihrt.BihrtError):
+        renderer.load_models(a).refit()                 # needs a full build first
+    renderer.build()
+    topo = renderer.reference_view()["children"].copy()
+    renderer.update_vertices(b)
+    renderer.refit()
+    v = renderer.reference_view()
+    np.testing.assert_array_equal(v["children"], topo)                      # same topology ...
+    rays = oracle.camera_rays(scenes.pinhole_camera(), 320, 180)
+    t, s, p = renderer.trace(rays)
+    # ... but bounds of the moved geometry: compare with brute force on the moved mesh, by primitive id
+    ob = oracle.Bih(b)
+    tb, sb, pb = ob.trace(rays, "brute")
+    np.testing.assert_array_equal(p, pb)
+    np.testing.assert_array_equal(t, tb)
+    renderer.build()                                                        # a full rebuild is the parity path again
+    from conftest import assert_view_equals_oracle
+    assert_view_equals_oracle(renderer.reference_view(), ob)
