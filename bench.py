@@ -195,7 +195,7 @@ def run_ours(args, rank, world, local_rank):
 
     fb_t = None
 
-    by_sample = world > 1 and spp >= world          # else tiles round-robin
+    by_sample = world > 1 and spp >= world and os.environ.get("BIHRT_BENCH_SHARD", "samples") != "tiles"   # else tiles round-robin
     s0, s1 = multi.sample_range(spp, rank, world)
 
     def render_my_share():

@@ -538,8 +538,18 @@ __global__ void __launch_bounds__(128) k_nodes(const uint32_t* __restrict__ umc,
                                             : BIH_REF_NODE(split + 1, (__clz(ms1 ^ __ldg(umc + b)) + 1) % 3);
     // leaves [a, split] are slots [first[a], first[split+1]); leaves [split+1, b] are [first[split+1], first[b+1])
     const uint32_t sa = __ldg(first + a), sm = __ldg(first + split + 1), sb = __ldg(first + b + 1);
-    const float cl0 = heap_range<true>(heaps + (size_t)axis * 2 * P, P, sa, sm - 1);
-    const float cl1 = heap_range<false>(heaps + (size_t)(3 + axis) * 2 * P, P, sm, sb - 1);
+    // both range queries walk their heaps in one loop so that up to four independent loads are in flight
+    const float* hmax = heaps + (size_t)axis * 2 * P;
+    const float* hmin = heaps + (size_t)(3 + axis) * 2 * P;
+    float cl0 = -INFINITY, cl1 = INFINITY;
+    uint32_t l0 = sa + P, r0 = sm + P, l1 = sm + P, r1 = sb + P;          // half-open [l, r) at the leaf level
+    while (l0 < r0 || l1 < r1) {
+        float a0 = -INFINITY, b0 = -INFINITY, a1 = INFINITY, b1 = INFINITY;
+        if (l0 < r0) { if (l0 & 1u) a0 = __ldg(hmax + l0++); if (r0 & 1u) b0 = __ldg(hmax + --r0); l0 >>= 1; r0 >>= 1; }
+        if (l1 < r1) { if (l1 & 1u) a1 = __ldg(hmin + l1++); if (r1 & 1u) b1 = __ldg(hmin + --r1); l1 >>= 1; r1 >>= 1; }
+        cl0 = fmaxf(cl0, fmaxf(a0, b0));
+        cl1 = fminf(cl1, fminf(a1, b1));
+    }
     *reinterpret_cast<float4*>(nodes + idx) = make_float4(cl0, cl1, __uint_as_float(ref_l), __uint_as_float(ref_r));
     if (idx == 0) hdr->root_axis = (uint32_t)axis;
 }
