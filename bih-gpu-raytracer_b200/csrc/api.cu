@@ -156,7 +156,6 @@ int bihrt_sync(bihrt_ctx* c) {
 int bihrt_set_option(bihrt_ctx* c, const char* name, int64_t v) {
     if (!c || !name) return BIHRT_ERR_INVALID;
     if (!strcmp(name, "trace_blocks_per_sm")) c->opt_trace_blocks_per_sm = (int)v;
-    else if (!strcmp(name, "trace_variant")) c->opt_trace_variant = (int)v;
     else if (!strcmp(name, "trace_refill_threshold")) c->opt_refill_threshold = (int)std::max<int64_t>(1, std::min<int64_t>(32, v));
     else if (!strcmp(name, "profile")) {
         c->opt_profile = (int)v;

@@ -43,8 +43,6 @@ struct __align__(16) BihTri {
     uint32_t slot;     // this record's own index (= the reference's HitRecord::triangleIdx)
 };
 
-struct SceneBox { float lo[3]; float hi[3]; };
-
 // Device-resident header of a built BIH; lives at the start of the blob that is broadcast.
 struct BihHeader {
     uint32_t n;          // triangles
@@ -101,15 +99,12 @@ struct bihrt_ctx {
     bool        build_timed = false;
 
     // options
-    int opt_trace_block = 128;
     int opt_trace_blocks_per_sm = 0;   // 0 = occupancy query
-    int opt_trace_variant = 0;
     int opt_refill_threshold = 32;
     int opt_refill_incoherent = 8;
     int opt_chunk_items = 32;
     int opt_vote_wait = 1, opt_vote_walk = 3;
     int opt_sm_queues = -1; // 1: per-SM work queues (tile locality in L1), 0: one global counter, -1: by launch size
-    int opt_sort_passes = 4;
     int64_t kernel_launches = 0;
     int opt_profile = 0;    // record an event after every build stage (bihrt_get_stat "build_stage_us_<i>")
     cudaEvent_t prof_ev[BIHRT_PROF_EVENTS] = {};

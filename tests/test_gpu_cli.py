@@ -1,0 +1,43 @@
+"""The C host program (bih-gpu-raytracer_b200/host/bihrt_cli.c): the reference's main / LoadModels / frame loop
+on top of the C ABI, checked against the Python mirror pixel for pixel."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(ROOT, "bih-gpu-raytracer_b200", "bihrt_cli")
+
+
+def read_ppm(path):
+    with open(path, "rb") as f:
+        assert f.readline().strip() == b"P6"
+        w, h = map(int, f.readline().split())
+        assert int(f.readline()) == 255
+        return np.frombuffer(f.read(), np.uint8).reshape(h, w, 3)
+
+
+@pytest.mark.skipif(not os.path.exists(CLI), reason="bihrt_cli not built")
+def test_cli_renders_like_the_library(renderer, scenes, tmp_path):
+    tri = (scenes.displaced_sphere(48) * np.float32(0.8) + np.tile(np.float32([2.4, 0.0, 0.0]), 3)).astype(np.float32)
+    raw = tmp_path / "mesh.tri9"
+    tri.tofile(raw)
+    out = tmp_path / "frame.ppm"
+    w, h, spp = 160, 120, 2
+    p = subprocess.run([CLI, str(raw), "-w", str(w), "-h", str(h), "-s", str(spp), "-o", str(out)],
+                       capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert "%d triangles" % len(tri) in p.stdout
+    img = read_ppm(out)
+    cam = scenes.reference_camera(aspect=w / h)                      # Camera((2,0,-2), W/H), R/src/Renderer.cpp:99
+    fb = renderer.load_models(tri).build().render(cam, w, h, spp=spp, seed=1984, jitter=True).framebuffer()
+    exp = np.stack([fb & 255, (fb >> 8) & 255, (fb >> 16) & 255], -1).astype(np.uint8)[::-1]   # row 0 = bottom
+    np.testing.assert_array_equal(img, exp)
+    assert (img[..., 2] == 0).any() and (img[..., 2] == 40).any()    # both hits (yellow) and misses in the frame
+
+
+def test_cli_reports_errors():
+    p = subprocess.run([CLI, "/nonexistent.obj"], capture_output=True, text=True, timeout=60)
+    assert p.returncode == 1 and "cannot open" in p.stderr
