@@ -8,7 +8,8 @@ Workload (config.workload): the 1 002 528-triangle displaced sphere of BASELINE 
 the north star's 70 % target is quoted on) seen by the config-2 camera, traced with config 4's ray
 load: 3840x2160 pixels x 16 jittered primary rays = 132 710 400 rays per step.  A step = one frame's
 trace with the BIH resident in HBM.  At N > 1 the frame's rays are partitioned over the ranks (strong
-scaling: total work fixed) -- by sample (rank r traces samples [16r/N, 16(r+1)/N) of every pixel) -- the
+scaling: total work fixed) -- by unit interleave (every rank walks every tile and owns every N-th 32-ray
+unit, i.e. a few neighbouring pixels with all their samples) -- the
 BIH built on rank 0 is replicated by one NCCL broadcast before the timed region, and every step ends
 with the framebuffer reduce to rank 0 (+ resolve of the hit counts to packed colours).
 
@@ -195,13 +196,22 @@ def run_ours(args, rank, world, local_rank):
 
     fb_t = None
 
-    by_sample = world > 1 and spp >= world and os.environ.get("BIHRT_BENCH_SHARD", "samples") != "tiles"   # else tiles round-robin
+    # N > 1: unit interleave (every rank walks every tile and owns every N-th 32-ray unit of it: balanced, and a
+    # pixel keeps all its samples in consecutive lanes); samples / tiles per rank are the fall-backs
+    mode = os.environ.get("BIHRT_BENCH_SHARD", "interleave") if world > 1 else "single"
+    if mode == "interleave" and (32 * (spp & -spp if spp & -spp < 32 else 32)) % world != 0:
+        mode = "samples"
+    if mode == "samples" and spp < world:
+        mode = "tiles"
+    by_sample = mode in ("samples", "interleave")        # per-pixel hit counts, resolved after the reduce
     s0, s1 = multi.sample_range(spp, rank, world)
 
     def render_my_share():
         if world == 1:
             r.render(cam, W, H, spp=spp, seed=1984, jitter=True)
-        elif by_sample:
+        elif mode == "interleave":
+            r.render_interleaved(cam, W, H, spp, rank, world, seed=1984, jitter=True)
+        elif mode == "samples":
             r.render_samples(cam, W, H, spp, s0, s1, seed=1984, jitter=True)
         else:
             r.render(cam, W, H, spp=spp, seed=1984, jitter=True, shard=(rank, world))
@@ -317,9 +327,11 @@ def run_ours(args, rank, world, local_rank):
                "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                "config": {"workload": name, "triangles": n_tri, "leaves": info["nu"], "rays_per_step": rays_total,
-                          "l2": "flushed before every timed step (256 MiB write)", "parallelism": ("samples%d" if by_sample else "tiles%d") % world,
-                          "sharding": ("samples of every pixel split over ranks (hit counts, reduce, resolve)" if by_sample else
-                                       "32x32-pixel tiles round-robin over ranks") + "; BIH broadcast once; framebuffer reduce per step"},
+                          "l2": "flushed before every timed step (256 MiB write)", "parallelism": "%s%d" % (mode, world),
+                          "sharding": {"single": "one GPU",
+                                       "interleave": "every rank walks every 32x32 tile and owns every N-th 32-ray unit (hit counts, reduce, resolve)",
+                                       "samples": "samples of every pixel split over ranks (hit counts, reduce, resolve)",
+                                       "tiles": "32x32-pixel tiles round-robin over ranks"}[mode] + "; BIH broadcast once; framebuffer reduce per step"},
                "build_ms_per_mtri": build_ms / (n_tri / 1e6), "build_ms": build_ms,
                "e2e": {"value": e2e_val, "unit": "Mrays/s", "h2d_bytes_per_step": n_tri * 36, "d2h_bytes_per_step": W * H * 4,
                        "ms_per_step": ms_e2e,

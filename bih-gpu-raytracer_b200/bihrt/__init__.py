@@ -65,7 +65,7 @@ ABI_SYMBOLS = [
     "bihrt_version", "bihrt_create", "bihrt_destroy", "bihrt_last_error", "bihrt_set_stream", "bihrt_sync",
     "bihrt_set_option", "bihrt_get_stat", "bihrt_scene_load_triangles", "bihrt_scene_update_vertices", "bihrt_scene_load_obj",
     "bihrt_build", "bihrt_refit", "bihrt_get_build_info", "bihrt_export_reference_view", "bihrt_trace", "bihrt_trace_counted",
-    "bihrt_render", "bihrt_render_counted", "bihrt_render_shard", "bihrt_render_samples", "bihrt_framebuffer_resolve", "bihrt_render_hits", "bihrt_secondary_rays", "bihrt_framebuffer", "bihrt_framebuffer_read",
+    "bihrt_render", "bihrt_render_counted", "bihrt_render_shard", "bihrt_render_samples", "bihrt_render_interleaved", "bihrt_framebuffer_resolve", "bihrt_render_hits", "bihrt_secondary_rays", "bihrt_framebuffer", "bihrt_framebuffer_read",
     "bihrt_bih_blob_bytes", "bihrt_bih_export", "bihrt_bih_import",
 ]
 
@@ -252,6 +252,14 @@ class Renderer:
         self._check(self._lib.bihrt_render_samples(self._ctx, C.byref(cam), C.c_int32(w), C.c_int32(h), C.c_int32(spp),
                                                    C.c_uint64(seed), C.c_uint32(RENDER_JITTER if jitter else 0),
                                                    C.c_int32(sample_begin), C.c_int32(sample_end)))
+        return self
+
+    def render_interleaved(self, camera, w, h, spp, index, count, seed=1984, jitter=True):
+        """Multi-GPU unit interleave: hit counts of every count-th 32-ray unit of every tile (bihrt_render_interleaved)."""
+        cam = camera if isinstance(camera, Camera) else Camera.from_array(camera)
+        self._check(self._lib.bihrt_render_interleaved(self._ctx, C.byref(cam), C.c_int32(w), C.c_int32(h), C.c_int32(spp),
+                                                       C.c_uint64(seed), C.c_uint32(RENDER_JITTER if jitter else 0),
+                                                       C.c_int32(index), C.c_int32(count)))
         return self
 
     def framebuffer_resolve(self, spp):

@@ -5,7 +5,9 @@ replicated tree, so the partition is data-parallel:
 
   * the BIH is built once on rank `src` and replicated with ONE broadcast of the blob
     [header | nodes | leaf-ordered triangles] (bihrt_bih_export / bihrt_bih_import);
-  * ray batches are partitioned either by SAMPLE (rank r traces samples [spp*r/G, spp*(r+1)/G) of every
+  * ray batches are partitioned by UNIT INTERLEAVE (preferred: every rank walks every 32x32 tile and traces every
+    G-th 32-ray unit of it -- a few neighbouring pixels with all their samples -- writing per-pixel hit counts,
+    bihrt_render_interleaved: balanced by construction, single-GPU locality, samples stay in consecutive lanes), by SAMPLE (rank r traces samples [spp*r/G, spp*(r+1)/G) of every
     pixel and stores per-pixel hit counts, bihrt_render_samples -- every rank walks the whole image, so
     the warps keep the single-GPU coherence; the default when spp >= G) or by TILE (32x32-pixel tiles
     dealt round-robin, tile k -> rank k mod G, other pixels 0, bihrt_render_shard; used when spp < G);

@@ -161,6 +161,7 @@ int bihrt_set_option(bihrt_ctx* c, const char* name, int64_t v) {
         c->opt_profile = (int)v;
         if (v) for (int i = 0; i < BIHRT_PROF_EVENTS; i++) if (!c->prof_ev[i]) cudaEventCreate(&c->prof_ev[i]);
     }
+    else if (!strcmp(name, "trace_lane_groups")) c->opt_lane_groups = (int)v;
     else if (!strcmp(name, "trace_sm_queues")) c->opt_sm_queues = (int)v;
     else if (!strcmp(name, "trace_vote_wait")) c->opt_vote_wait = (int)v;
     else if (!strcmp(name, "trace_vote_walk")) c->opt_vote_walk = (int)v;
@@ -370,7 +371,7 @@ static void base_args(bihrt_ctx* c, TraceArgs& a) {
     memset(&a, 0, sizeof a);
     a.hdr = c->d_hdr; a.nodes = c->d_nodes; a.tris = c->d_tris;
     a.counters = c->d_counters; a.work = c->d_work;
-    a.shard_index = 0; a.shard_count = 1;
+    a.shard_index = 0; a.shard_count = 1; a.il_index = 0; a.il_count = 1;
     a.refill_threshold = c->opt_refill_threshold; a.chunk_items = c->opt_chunk_items;
     a.refill_incoherent = c->opt_refill_incoherent;
     a.vote_wait = c->opt_vote_wait; a.vote_walk = c->opt_vote_walk;
@@ -447,8 +448,17 @@ static int render_check(bihrt_ctx* c, const bihrt_camera* cam, int w, int h, int
     return BIHRT_OK;
 }
 
+// samples of one pixel laid along consecutive lanes: the largest power of two that divides the sample count (<= 32)
+static int pick_gshift(bihrt_ctx* c, int nsamples) {
+    int g = 0;
+    while (g < 5 && nsamples > 0 && (nsamples & ((2 << g) - 1)) == 0) g++;
+    if (c->opt_lane_groups >= 0) { int want = 0; while ((2 << want) <= c->opt_lane_groups) want++; g = std::min(g, want); }
+    return g;
+}
+
 static int render_impl(bihrt_ctx* c, const bihrt_camera* cam, int32_t w, int32_t h, int32_t spp, uint64_t seed, uint32_t flags,
-                       int32_t shard_index, int32_t shard_count, uint64_t* counters, int32_t s_begin = 0, int32_t s_end = -1) {
+                       int32_t shard_index, int32_t shard_count, uint64_t* counters, int32_t s_begin = 0, int32_t s_end = -1,
+                       int32_t il_index = 0, int32_t il_count = 1) {
     ENTER(c);
     if (s_end < 0) s_end = spp;
     if (s_begin < 0 || s_begin > s_end || s_end > spp) return bihrt_fail(c, BIHRT_ERR_INVALID, "bad sample range [%d,%d) of %d", s_begin, s_end, spp);
@@ -462,13 +472,26 @@ static int render_impl(bihrt_ctx* c, const bihrt_camera* cam, int32_t w, int32_t
     a.cam = *cam; a.w = w; a.h = h; a.spp = spp; a.seed = seed; a.flags = flags;
     a.shard_index = shard_index; a.shard_count = shard_count; a.fb = c->d_fb;
     a.s_begin = s_begin; a.s_end = s_end;
+    a.gshift = (shard_count > 1) ? 0 : pick_gshift(c, s_end - s_begin);       // tile shards keep "other pixels are 0"
+    a.il_index = il_index; a.il_count = il_count;
+    if (il_count > 1) {
+        if (il_index < 0 || il_index >= il_count || ((32 << a.gshift) % il_count) != 0)
+            return bihrt_fail(c, BIHRT_ERR_INVALID, "interleave %d of %d does not divide the %d units of a tile", il_index, il_count, 32 << a.gshift);
+        if (a.gshift == 0) BIHRT_CUDA(c, cudaMemsetAsync(c->d_fb, 0, px * 4, c->stream));   // pixels of the other ranks stay 0
+    }
+    if (a.gshift > 0) BIHRT_CUDA(c, cudaMemsetAsync(c->d_fb, 0, px * 4, c->stream));   // hit counts are accumulated with atomics
     if (s_begin == s_end) {            // nothing to trace on this rank: all counts are 0
         BIHRT_CUDA(c, cudaMemsetAsync(c->d_fb, 0, px * 4, c->stream));
         return BIHRT_OK;
     }
-    if (!counters) return bihrt_trace_launch(c, a, 1, false);
+    const bool resolve = a.gshift > 0 && !(flags & BIHRT_RENDER_COUNTS);
+    if (!counters) {
+        if ((rc = bihrt_trace_launch(c, a, 1, false))) return rc;
+        return resolve ? bihrt_resolve_launch(c, c->d_fb, (int)px, s_end - s_begin) : BIHRT_OK;
+    }
     BIHRT_CUDA(c, cudaMemsetAsync(c->d_counters, 0, 32, c->stream));
     if ((rc = bihrt_trace_launch(c, a, 1, true))) return rc;
+    if (resolve && (rc = bihrt_resolve_launch(c, c->d_fb, (int)px, s_end - s_begin))) return rc;
     unsigned long long hc[4];
     BIHRT_CUDA(c, cudaMemcpyAsync(hc, c->d_counters, 32, cudaMemcpyDeviceToHost, c->stream));
     BIHRT_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -484,6 +507,11 @@ int bihrt_render_shard(bihrt_ctx* c, const bihrt_camera* cam, int32_t w, int32_t
 int bihrt_render_samples(bihrt_ctx* c, const bihrt_camera* cam, int32_t w, int32_t h, int32_t spp, uint64_t seed, uint32_t flags,
                          int32_t sample_begin, int32_t sample_end) {
     return render_impl(c, cam, w, h, spp, seed, flags | BIHRT_RENDER_COUNTS, 0, 1, nullptr, sample_begin, sample_end);
+}
+
+int bihrt_render_interleaved(bihrt_ctx* c, const bihrt_camera* cam, int32_t w, int32_t h, int32_t spp, uint64_t seed, uint32_t flags,
+                             int32_t index, int32_t count) {
+    return render_impl(c, cam, w, h, spp, seed, flags | BIHRT_RENDER_COUNTS, 0, 1, nullptr, 0, -1, index, count);
 }
 
 int bihrt_framebuffer_resolve(bihrt_ctx* c, int32_t spp) {
@@ -513,7 +541,7 @@ int bihrt_render_hits(bihrt_ctx* c, const bihrt_camera* cam, int32_t w, int32_t 
     if ((rc = stage_outputs(c, n, 0, t, slot, prim, o, &front))) return rc;
     TraceArgs a; base_args(c, a);
     a.cam = *cam; a.w = w; a.h = h; a.spp = spp; a.seed = seed; a.flags = flags;
-    a.s_begin = 0; a.s_end = spp;
+    a.s_begin = 0; a.s_end = spp; a.gshift = pick_gshift(c, spp);
     a.out_t = o.t; a.out_slot = o.slot; a.out_prim = o.prim;
     if ((rc = bihrt_trace_launch(c, a, 2, false))) return rc;
     return unstage_outputs(c, n, o);
@@ -539,7 +567,7 @@ int bihrt_secondary_rays(bihrt_ctx* c, const bihrt_camera* cam, int32_t w, int32
     uint32_t* d_cnt = (uint32_t*)((uint8_t*)c->d_io + (size_t)n * 8);
     TraceArgs a; base_args(c, a);
     a.cam = *cam; a.w = w; a.h = h; a.spp = spp; a.seed = seed; a.flags = flags;
-    a.s_begin = 0; a.s_end = spp;
+    a.s_begin = 0; a.s_end = spp; a.gshift = pick_gshift(c, spp);
     a.out_t = d_t; a.out_slot = d_slot; a.out_prim = nullptr;
     if ((rc = bihrt_trace_launch(c, a, 2, false))) return rc;
     if ((rc = bihrt_secondary_launch(c, d_t, d_slot, n, d_cnt, c->d_counters + 3, *cam, w, h, spp, seed, flags, kind, light, out_rays, out_sample))) return rc;

@@ -98,9 +98,13 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
         tx = (a.w + 31) / 32;
         const int ty = (a.h + 31) / 32, T = tx * ty;
         const int my_tiles = T > a.shard_index ? (T - a.shard_index + a.shard_count - 1) / a.shard_count : 0;
-        total = (uint64_t)my_tiles * 1024u;
+        total = ((uint64_t)my_tiles * 1024u) << a.gshift;
     }
-    const int nsamp = MODE == 0 ? 1 : (a.s_end - a.s_begin);     // samples of each pixel traced by this launch
+    // Camera modes: the samples [s_begin, s_end) of a pixel are split into 2^gshift groups that sit in
+    // CONSECUTIVE LANES (item = pixel * groups + group); a lane traces its group's samples one after the
+    // other.  More groups = a warp covers fewer pixels = its 32 rays are closer together.
+    const int gshift = MODE == 0 ? 0 : a.gshift;
+    const int nsamp = MODE == 0 ? 1 : ((a.s_end - a.s_begin) >> gshift);    // samples per item
     uint32_t my_queue = 0;
     if (a.queues > 1) { asm("mov.u32 %0, %%smid;" : "=r"(my_queue)); my_queue %= (uint32_t)a.queues; }
     uint64_t pool_next = 0, pool_end = 0;      // warp-uniform
@@ -108,7 +112,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
 
     // lane state
     uint64_t item = ~0ull;                     // current work item, ~0 = none
-    int s = 0;                                 // sample of the item being traced
+    int s = 0, s0 = 0;                         // sample of the item being traced, first sample of the item
     uint32_t hits = 0, pixel = 0, pxy = 0;
     float ox = 0.f, oy = 0.f, oz = 0.f, dx = 1.f, dy = 1.f, dz = 1.f;
     uint32_t cur = NONE;                       // item being walked: node index, leaf|slot, or NONE
@@ -141,14 +145,15 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
                     tracing = false;
                     if (MODE == 1) hits += (h.slot >= 0);
                     else {
-                        const uint64_t o = MODE == 0 ? item : (uint64_t)pixel * (uint32_t)a.spp + (uint32_t)(a.s_begin + s);
+                        const uint64_t o = MODE == 0 ? item : (uint64_t)pixel * (uint32_t)a.spp + (uint32_t)(s0 + s);
                         if (a.out_t) a.out_t[o] = h.t;
                         if (a.out_slot) a.out_slot[o] = h.slot;
                         if (a.out_prim) a.out_prim[o] = h.slot >= 0 ? (int32_t)tris[h.slot].prim : -1;
                     }
                     s++;
                     if (s == nsamp) {
-                        if (MODE == 1 && (a.flags & BIHRT_RENDER_COUNTS)) a.fb[pixel] = hits;     // resolved after the reduce
+                        if (MODE == 1 && gshift > 0) { if (hits) atomicAdd(&a.fb[pixel], hits); }       // zeroed before, resolved after
+                        else if (MODE == 1 && (a.flags & BIHRT_RENDER_COUNTS)) a.fb[pixel] = hits;     // resolved after the reduce
                         else if (MODE == 1) {
                             // Color + rgbToInt, R/src/CUDAKernels.cu:82-88,385-387,420-422 (sums of 255/20/40 are exact)
                             const float fh = (float)hits, fm = (float)(nsamp - (int)hits), fs = (float)nsamp;
@@ -176,19 +181,27 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
                     uint64_t base = ~0ull;
                     uint32_t got = 0;
                     if (lane == 0) {
+                        // unit interleave across GPUs (il_count ranks): this rank owns every il_count-th 32-item unit
+                        // of every tile, so all ranks walk all tiles (same locality, perfect balance) and every
+                        // pixel keeps all its samples -- and their lane grouping -- on one GPU
+                        const uint32_t ilc = (uint32_t)a.il_count, ili = (uint32_t)a.il_index;
                         if (a.queues <= 1) {
-                            base = atomicAdd(a.work, (uint32_t)a.chunk_items); got = (uint32_t)a.chunk_items;
+                            const uint32_t chunk = ilc > 1 ? 32u : (uint32_t)a.chunk_items;
+                            const uint64_t fetched = atomicAdd(a.work, chunk); got = chunk;
+                            base = ilc > 1 ? ((fetched >> 5) * ilc + ili) << 5 : fetched;
                             if (base >= total) base = ~0ull;
                         } else {
-                            const uint64_t ntile = (total + 1023) >> 10;
+                            const uint32_t tshift = 10 + gshift, ushift = 5 + gshift;       // items / units per tile
+                            const uint64_t ntile = (total + ((1ull << tshift) - 1)) >> tshift;
                             for (uint32_t k = 0; k < (uint32_t)a.queues; k++) {
                                 uint32_t q = my_queue + k; if (q >= (uint32_t)a.queues) q -= (uint32_t)a.queues;
                                 if (q >= ntile) continue;
-                                const uint64_t units = ((ntile - q + a.queues - 1) / a.queues) * 32;       // of queue q
+                                const uint32_t upt = (1u << ushift) / ilc;                                  // this rank's units per tile
+                                const uint64_t units = ((ntile - q + a.queues - 1) / a.queues) * upt;       // of queue q
                                 if (ld_relaxed(a.work + q) >= units) continue;
                                 const uint32_t u = atomicAdd(a.work + q, 1u);
                                 if (u >= units) continue;
-                                const uint64_t b = (((uint64_t)(u >> 5) * a.queues + q) << 10) + ((u & 31u) << 5);
+                                const uint64_t b = (((uint64_t)(u / upt) * a.queues + q) << tshift) + ((uint64_t)((u % upt) * ilc + ili) << 5);
                                 if (b < total) { base = b; got = 32; break; }
                             }
                         }
@@ -205,7 +218,9 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
                 if (served) {
                     item = pool_next + rank; s = 0; hits = 0; want_item = false;
                     if (MODE != 0) {
-                        const uint32_t m = (uint32_t)(item >> 10), q = (uint32_t)item & 1023u;
+                        const uint64_t pix = item >> gshift;
+                        s0 = a.s_begin + (int)((uint32_t)item & ((1u << gshift) - 1u)) * nsamp;
+                        const uint32_t m = (uint32_t)(pix >> 10), q = (uint32_t)pix & 1023u;
                         const int tile = a.shard_index + (int)m * a.shard_count;
                         const int px = (tile % tx) * 32 + (int)((q >> 5) & 3u) * 8 + (int)(q & 7u);
                         const int py = (tile / tx) * 32 + (int)(q >> 7) * 4 + (int)((q >> 3) & 3u);
@@ -226,8 +241,8 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
                 } else {
                     // u,v per R/src/CUDAKernels.cu:414-415; GetRay per R/src/Camera.cu:18-20
                     const int px = (int)(pxy & 0xFFFFu), py = (int)(pxy >> 16);
-                    const float ru = (a.flags & BIHRT_RENDER_JITTER) ? bihrt_jitter(a.seed, pixel, (uint32_t)(a.s_begin + s), 0) : 0.5f;
-                    const float rv = (a.flags & BIHRT_RENDER_JITTER) ? bihrt_jitter(a.seed, pixel, (uint32_t)(a.s_begin + s), 1) : 0.5f;
+                    const float ru = (a.flags & BIHRT_RENDER_JITTER) ? bihrt_jitter(a.seed, pixel, (uint32_t)(s0 + s), 0) : 0.5f;
+                    const float rv = (a.flags & BIHRT_RENDER_JITTER) ? bihrt_jitter(a.seed, pixel, (uint32_t)(s0 + s), 1) : 0.5f;
                     const float uu = __fdiv_rn(__fadd_rn((float)px, ru), (float)a.w);
                     const float vv = __fdiv_rn(__fadd_rn((float)py, rv), (float)a.h);
                     ox = a.cam.origin[0]; oy = a.cam.origin[1]; oz = a.cam.origin[2];
@@ -405,7 +420,7 @@ int bihrt_trace_launch(bihrt_ctx* c, const TraceArgs& a_in, int mode, bool count
     TraceArgs a = a_in;
     // per-SM queues pay off once a launch is long enough to amortise the end-of-kernel stealing
     // (measured: +7 % at 133 M rays, -9 % at 2 M rays on the 1 M-triangle scene)
-    const int64_t rays = mode == 0 ? a.nrays : (int64_t)a.w * a.h * (a.s_end - a.s_begin) / (a.shard_count > 0 ? a.shard_count : 1);
+    const int64_t rays = mode == 0 ? a.nrays : (int64_t)a.w * a.h * (a.s_end - a.s_begin) / (a.shard_count > 0 ? a.shard_count : 1) / (a.il_count > 0 ? a.il_count : 1);
     const bool on = a.queues < 0 ? rays >= (16ll << 20) : a.queues != 0;
     a.queues = on ? (c->sm_count < 1024 ? c->sm_count : 1024) : 1;
     switch (mode * 2 + (counted ? 1 : 0)) {

@@ -160,6 +160,12 @@ BIHRT_API int bihrt_render_shard(bihrt_ctx* ctx, const bihrt_camera* cam, int32_
 BIHRT_API int bihrt_render_samples(bihrt_ctx* ctx, const bihrt_camera* cam, int32_t w, int32_t h, int32_t spp,
                          uint64_t seed, uint32_t flags, int32_t sample_begin, int32_t sample_end);
 BIHRT_API int bihrt_framebuffer_resolve(bihrt_ctx* ctx, int32_t spp);   /* counts -> packed colours, in place */
+/* Multi-GPU, unit interleave (preferred): every rank walks every 32x32 tile but traces only every count-th
+ * 32-ray unit of it (unit = a few neighbouring pixels with ALL their samples), writing per-pixel hit counts and 0
+ * for the pixels it does not own.  Balanced by construction, same tile locality as the single-GPU render, and a
+ * pixel's samples stay together in consecutive lanes.  count must divide 32 << k, k = log2 of the lane groups. */
+BIHRT_API int bihrt_render_interleaved(bihrt_ctx* ctx, const bihrt_camera* cam, int32_t w, int32_t h, int32_t spp,
+                             uint64_t seed, uint32_t flags, int32_t index, int32_t count);
 /* Per-sample hit buffers of the same rays bihrt_render traces (index = (j*w+i)*spp + s); device or
  * host outputs, any may be NULL.  Used by the parity tests. */
 BIHRT_API int bihrt_render_hits(bihrt_ctx* ctx, const bihrt_camera* cam, int32_t w, int32_t h, int32_t spp,

@@ -151,6 +151,21 @@ def test_render_hits_framebuffer_and_shards(renderer, scenes, oracle):
     multi.framebuffer_tensor(renderer).copy_(counts)
     torch.cuda.synchronize()
     np.testing.assert_array_equal(renderer.framebuffer_resolve(spp).framebuffer(), full)
+    # unit interleave: every rank walks every tile, owns every count-th 32-ray unit; disjoint pixels
+    for count in (2, 4, 8):
+        counts.zero_()
+        owned = torch.zeros((h, w), dtype=torch.int32, device="cuda")
+        for k in range(count):
+            renderer.render_interleaved(cam, w, h, spp, k, count, jitter=True)
+            renderer.sync()
+            part = multi.framebuffer_tensor(renderer)
+            counts += part
+            owned += (part > 0).int()
+            torch.cuda.synchronize()
+        assert int(owned.max()) <= 1
+        multi.framebuffer_tensor(renderer).copy_(counts)
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(renderer.framebuffer_resolve(spp).framebuffer(), full)
 
 
 def test_bih_blob_roundtrip(scenes, oracle):
