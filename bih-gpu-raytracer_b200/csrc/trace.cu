@@ -152,7 +152,13 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
                     }
                     s++;
                     if (s == nsamp) {
-                        if (MODE == 1 && gshift > 0) { if (hits) atomicAdd(&a.fb[pixel], hits); }       // zeroed before, resolved after
+                        if (MODE == 1 && gshift > 0) {
+                            // the lanes of one pixel finish together: one atomic per pixel and warp (fb zeroed before, resolved after)
+                            const uint32_t am = __activemask();
+                            const uint32_t same = __match_any_sync(am, pixel);
+                            const uint32_t sum = __reduce_add_sync(same, hits);
+                            if (sum && lane == __ffs(same) - 1) atomicAdd(&a.fb[pixel], sum);
+                        }
                         else if (MODE == 1 && (a.flags & BIHRT_RENDER_COUNTS)) a.fb[pixel] = hits;     // resolved after the reduce
                         else if (MODE == 1) {
                             // Color + rgbToInt, R/src/CUDAKernels.cu:82-88,385-387,420-422 (sums of 255/20/40 are exact)
