@@ -272,6 +272,18 @@ def run_ours(args, rank, world, local_rank):
         breakdown = {"render_shard_ms_max_over_ranks": t_r, "framebuffer_reduce_ms": t_g}
         barrier()
 
+    # ---- N > 1: the gathered frame must be bit-identical to the single-GPU render ------------------
+    image_ok = None
+    if world > 1:
+        with torch.cuda.stream(stream):
+            step()
+        barrier()
+        if rank == 0:
+            multi_fb = r.framebuffer().copy()
+            single_fb = r.render(cam, W, H, spp=spp, seed=1984, jitter=True).framebuffer()
+            image_ok = bool(np.array_equal(multi_fb, single_fb))
+        barrier()
+
     # ---- e2e: the reference's full frame through the C ABI with host buffers -----------------------
     host_fb = torch.empty((H, W), dtype=torch.int32).pin_memory() if rank == 0 else None
 
@@ -340,6 +352,7 @@ def run_ours(args, rank, world, local_rank):
                "gpu_launches": int(launches), "clocks": clocks}
         if breakdown:
             out["breakdown"] = breakdown
+            out["multi_gpu_image_bit_identical_to_single_gpu"] = image_ok
         if roofline:
             out["roofline"] = roofline
 

@@ -1,0 +1,49 @@
+"""Two GPUs in one process (no NCCL): BIH blob replicated to the second device, frame split by unit interleave /
+samples / tiles, shards summed and resolved -- bit-identical to the single-GPU image.
+Skipped on a one-GPU box; the N = 2/4/8 torchrun path is exercised by bench.py, which reports the same check."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_two_gpus_render_the_same_image(scenes):
+    import torch
+    import bihrt
+    from bihrt import multi
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    tri = scenes.displaced_sphere(128)
+    cam = scenes.pinhole_camera(aspect=320 / 200)
+    w, h, spp = 320, 200, 8
+    r0, r1 = bihrt.Renderer(0), bihrt.Renderer(1)
+    r0.load_models(tri).build()
+    full = r0.render(cam, w, h, spp=spp, jitter=True).framebuffer().copy()
+    # replicate: export on device 0, copy across, import on device 1
+    nbytes = r0.bih_blob_bytes()
+    blob0 = torch.empty(nbytes, dtype=torch.uint8, device="cuda:0")
+    r0.bih_export(blob0, nbytes); r0.sync()
+    blob1 = blob0.to("cuda:1")
+    torch.cuda.synchronize(1)
+    r1.bih_import(blob1, nbytes); r1.sync()
+    for mode in ("interleave", "samples", "tiles"):
+        parts = []
+        for rank, r in ((0, r0), (1, r1)):
+            if mode == "interleave":
+                r.render_interleaved(cam, w, h, spp, rank, 2, jitter=True)
+            elif mode == "samples":
+                s0, s1 = multi.sample_range(spp, rank, 2)
+                r.render_samples(cam, w, h, spp, s0, s1, jitter=True)
+            else:
+                r.render(cam, w, h, spp=spp, jitter=True, shard=(rank, 2))
+            parts.append(r.framebuffer().astype(np.int64))
+        total = (parts[0] + parts[1]).astype(np.uint32)
+        if mode == "tiles":
+            np.testing.assert_array_equal(total, full)
+        else:
+            r0.render_samples(cam, w, h, spp, 0, spp, jitter=True); r0.sync()      # any frame of the right size
+            torch.cuda.synchronize(0)
+            multi.framebuffer_tensor(r0).copy_(torch.from_numpy(total.astype(np.int32)).to("cuda:0"))
+            torch.cuda.synchronize(0)
+            np.testing.assert_array_equal(r0.framebuffer_resolve(spp).framebuffer(), full)
+    r0.close(); r1.close()
