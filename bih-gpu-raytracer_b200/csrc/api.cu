@@ -71,6 +71,7 @@ static int ensure_capacity(bihrt_ctx* c, int64_t n, bool with_build_scratch) {
         dev_free(&c->d_umc); dev_free(&c->d_first); dev_free(&c->d_lookback); dev_free(&c->d_heaps);
         c->cap_n = cap;
         c->have_scene = false; c->built = false;
+        if (c->build_graph_exec) { cudaGraphExecDestroy(c->build_graph_exec); c->build_graph_exec = nullptr; }
         bind_blob(c, cap);
     }
     if (with_build_scratch && !c->d_keys[0]) {
@@ -133,6 +134,7 @@ void bihrt_destroy(bihrt_ctx* c) {
     if (c->d_io) { cudaFree(c->d_io); c->d_io = nullptr; }
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->build_graph_exec) cudaGraphExecDestroy(c->build_graph_exec);
     for (int i = 0; i < BIHRT_PROF_EVENTS; i++) if (c->prof_ev[i]) cudaEventDestroy(c->prof_ev[i]);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
@@ -157,6 +159,7 @@ int bihrt_set_option(bihrt_ctx* c, const char* name, int64_t v) {
     if (!c || !name) return BIHRT_ERR_INVALID;
     if (!strcmp(name, "trace_blocks_per_sm")) c->opt_trace_blocks_per_sm = (int)v;
     else if (!strcmp(name, "trace_refill_threshold")) c->opt_refill_threshold = (int)std::max<int64_t>(1, std::min<int64_t>(32, v));
+    else if (!strcmp(name, "build_graph")) c->opt_build_graph = (int)v;
     else if (!strcmp(name, "profile")) {
         c->opt_profile = (int)v;
         if (v) for (int i = 0; i < BIHRT_PROF_EVENTS; i++) if (!c->prof_ev[i]) cudaEventCreate(&c->prof_ev[i]);
@@ -266,6 +269,27 @@ int bihrt_build(bihrt_ctx* c) {
     BIHRT_CUDA(c, cudaEventRecord(c->ev0, c->stream));
     if (c->n == 0) {
         BIHRT_CUDA(c, cudaMemsetAsync(c->d_hdr, 0, sizeof(BihHeader), c->stream));
+    } else if (c->opt_build_graph && !c->opt_profile) {
+        // The build is ~16 short launches with fixed arguments for a given triangle count: capture them once
+        // into a CUDA graph and replay it (the reference rebuilds every frame, R/src/Renderer.cpp:415-503).
+        if (!c->build_graph_exec || c->build_graph_n != c->n) {
+            if (c->build_graph_exec) { cudaGraphExecDestroy(c->build_graph_exec); c->build_graph_exec = nullptr; }
+            cudaGraph_t g = nullptr;
+            BIHRT_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+            const int64_t launches_before = c->kernel_launches;
+            int rc = bihrt_build_launch(c);
+            cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+            if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+            if (e != cudaSuccess) return bihrt_fail(c, BIHRT_ERR_CUDA, "graph capture of the build failed: %s", cudaGetErrorString(e));
+            e = cudaGraphInstantiate(&c->build_graph_exec, g, 0);
+            cudaGraphDestroy(g);
+            if (e != cudaSuccess) { c->build_graph_exec = nullptr; return bihrt_fail(c, BIHRT_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e)); }
+            c->build_graph_n = c->n;
+            c->build_graph_launches = c->kernel_launches - launches_before;
+            c->kernel_launches = launches_before;             // nothing ran during capture
+        }
+        BIHRT_CUDA(c, cudaGraphLaunch(c->build_graph_exec, c->stream));
+        c->kernel_launches += c->build_graph_launches;
     } else {
         int rc = bihrt_build_launch(c);
         if (rc) return rc;

@@ -107,6 +107,8 @@ struct bihrt_ctx {
     int opt_lane_groups = -1; // samples of a pixel across lanes: -1 auto (as many as divide the sample count, <= 32), else 2^k
     int opt_sm_queues = -1; // 1: per-SM work queues (tile locality in L1), 0: one global counter, -1: by launch size
     int64_t kernel_launches = 0;
+    int opt_build_graph = 1;            // replay the build as a captured CUDA graph
+    cudaGraphExec_t build_graph_exec = nullptr; int64_t build_graph_n = -1, build_graph_launches = 0;
     int opt_profile = 0;    // record an event after every build stage (bihrt_get_stat "build_stage_us_<i>")
     cudaEvent_t prof_ev[BIHRT_PROF_EVENTS] = {};
     int prof_count = 0;
