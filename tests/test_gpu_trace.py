@@ -261,3 +261,24 @@ def test_ten_million_triangles(renderer, scenes, oracle):
     t, s, p = renderer.trace(rays)
     t0, s0, p0 = ob.trace(rays, "ref")
     compare(t, s, p, t0, s0, p0)
+
+
+@pytest.mark.parametrize("spp", [1, 3, 6, 12, 32, 40])
+def test_sample_counts_and_lane_groups(renderer, scenes, oracle, spp):
+    """Any sample count: the samples of a pixel are split over 2^k lanes (k = largest power of two dividing
+    spp, at most 32 lanes) -- the image and the per-sample hits must not depend on the grouping."""
+    tri = scenes.displaced_sphere(64)
+    cam = scenes.pinhole_camera(aspect=96 / 64)
+    w, h = 96, 64
+    ob = oracle.Bih(tri)
+    renderer.load_models(tri).build()
+    rays = oracle.camera_rays(cam, w, h, spp=spp, jitter=True, seed=7)
+    t0, s0, p0 = ob.trace(rays, "ref")
+    exp = oracle.pack_framebuffer(s0, w, h, spp).reshape(h, w)
+    for groups in (-1, 1, 2):
+        renderer.set_option("trace_lane_groups", groups)
+        fb = renderer.render(cam, w, h, spp=spp, seed=7, jitter=True).framebuffer()
+        np.testing.assert_array_equal(fb, exp)
+        t, s, p = renderer.render_hits(cam, w, h, spp=spp, seed=7, jitter=True)
+        np.testing.assert_array_equal(s, s0)
+        np.testing.assert_array_equal(t, t0)
