@@ -379,6 +379,12 @@ def run_ours(args, rank, world, local_rank):
                 bms = med(lambda: r.build())
                 e = {"triangles": len(t2), "leaves": r.build_info()["nu"], "build_ms": bms, "build_ms_per_mtri": bms / (len(t2) / 1e6),
                      "primary_mrays_s_1080p_1spp": primary(c2, 1920, 1080, 1), "primary_mrays_s_1080p_4spp": primary(c2, 1920, 1080, 4)}
+                cc = r.render_counted(c2, 1920, 1080, spp=1)
+                bpr = cc["nodes"] / cc["rays"] * 16 + cc["tris"] / cc["rays"] * 48 + 4.0
+                pk = peaks()[0]
+                e.update({"nodes_per_ray": cc["nodes"] / cc["rays"], "tris_per_ray": cc["tris"] / cc["rays"], "algorithmic_bytes_per_ray": bpr,
+                          "roofline_frac_1080p_1spp": e["primary_mrays_s_1080p_1spp"] * 1e6 * bpr / (pk * 1e9),
+                          "roofline_frac_1080p_4spp": e["primary_mrays_s_1080p_4spp"] * 1e6 * bpr / (pk * 1e9)})
                 if key == "1m":      # config 5: animated frame = rebuild + trace, 1080p
                     tms = med(lambda: r.render(c2, 1920, 1080, spp=1))
                     fms = med(lambda: (r.build(), r.render(c2, 1920, 1080, spp=1)))
