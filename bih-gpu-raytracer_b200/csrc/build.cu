@@ -143,10 +143,13 @@ __device__ __forceinline__ uint32_t morton_of_tri(const float* t, const float sl
     return xx * 4 + yy * 2 + zz;
 }
 
-// warp-aggregated histogram update: coherent meshes put whole warps into one bin
+// histogram update: the two high digits are nearly uniform across a warp of neighbouring triangles (one
+// match_any + one shared atomic per distinct value); the two low digits are spread, plain shared atomics
 __device__ __forceinline__ void hist_add(uint32_t* s_hist, uint32_t code, uint32_t act, int lane) {
+    atomicAdd(&s_hist[code & 255u], 1u);
+    atomicAdd(&s_hist[256 + ((code >> 8) & 255u)], 1u);
 #pragma unroll
-    for (int p = 0; p < 4; p++) {
+    for (int p = 2; p < 4; p++) {
         const uint32_t d = (code >> (8 * p)) & 255u;
         const uint32_t peers = __match_any_sync(act, d);
         if (lane == __ffs(peers) - 1) atomicAdd(&s_hist[p * 256 + d], __popc(peers));
