@@ -44,8 +44,28 @@ __device__ __forceinline__ uint32_t block_excl_scan_256(uint32_t v, uint32_t* s_
     return base + inc - v;
 }
 
-// The streaming kernels read the input 4 triangles (36 floats = 9 x 16 B, 144 B, 16-byte aligned) per
-// thread with nine independent 128-bit loads in flight; a warp covers 4.6 KB contiguous per iteration.
+// The streaming kernels read the input 4 triangles ("quad": 36 floats = 9 x 16 B, 144 B, 16-byte aligned) per
+// thread.  A warp loads its 32 quads (4608 contiguous bytes) with nine fully coalesced 128-bit loads and
+// transposes them through a per-warp shared-memory buffer (lane-strided 128-bit global loads would touch 32
+// different lines per instruction and run at half the DRAM rate).  `quad0` = first quad of the warp.
+__device__ __forceinline__ void load_quads_warp(const float* __restrict__ tri, uint32_t quad0, uint32_t nq, float4* s_warp, int lane, float v[36]) {
+    const float4* p = reinterpret_cast<const float4*>(tri) + (size_t)quad0 * 9;
+    const uint32_t nvec = min(32u, nq - quad0) * 9u;                 // 16-byte vectors this warp owns
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 9; i++) {
+        const uint32_t j = i * 32 + lane;
+        if (j < nvec) s_warp[j] = __ldcs(p + j);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 9; i++) {                                    // lane reads vectors 9*lane .. 9*lane+8 (odd stride: conflict-free)
+        const float4 f = s_warp[9 * lane + i];
+        v[4 * i] = f.x; v[4 * i + 1] = f.y; v[4 * i + 2] = f.z; v[4 * i + 3] = f.w;
+    }
+}
+
+// k_morton is bound by its divisions and histogram atomics, not by the loads: plain per-thread 128-bit loads
 __device__ __forceinline__ void load_quad(const float* __restrict__ tri, uint32_t q, float v[36]) {
     const float4* p = reinterpret_cast<const float4*>(tri) + (size_t)q * 9;
 #pragma unroll
@@ -81,13 +101,17 @@ __global__ void k_init(uint32_t* hist, uint32_t* enc, BihHeader* hdr, uint32_t n
 // std::minmax order dependence; it cannot change any Morton code or hit.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_scene_box(const float* __restrict__ tri, uint32_t n, uint32_t* __restrict__ enc) {
+    __shared__ float4 s_stage[8][288];
     float lo[3] = { INFINITY, INFINITY, INFINITY }, hi[3] = { -INFINITY, -INFINITY, -INFINITY };
     const uint32_t nq = n >> 2;
-    for (uint32_t q = blockIdx.x * 256u + threadIdx.x; q < nq; q += gridDim.x * 256u) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t q0 = blockIdx.x * 256u + (threadIdx.x & ~31u); q0 < nq; q0 += gridDim.x * 256u) {
         float v[36];
-        load_quad(tri, q, v);
+        load_quads_warp(tri, q0, nq, s_stage[warp], lane, v);
+        if (q0 + lane < nq) {
 #pragma unroll
-        for (int i = 0; i < 36; i++) { lo[i % 3] = fminf(lo[i % 3], v[i]); hi[i % 3] = fmaxf(hi[i % 3], v[i]); }
+            for (int i = 0; i < 36; i++) { lo[i % 3] = fminf(lo[i % 3], v[i]); hi[i % 3] = fmaxf(hi[i % 3], v[i]); }
+        }
     }
     if (blockIdx.x == 0 && threadIdx.x < 9u * (n & 3u)) {           // the last n % 4 triangles
         const float f = tri[(size_t)nq * 36 + threadIdx.x];
