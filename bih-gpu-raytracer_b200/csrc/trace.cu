@@ -75,7 +75,9 @@ __device__ __forceinline__ void test_leaf(const char* __restrict__ first_tri, fl
 // MODE 0: ray list -> (t, slot, prim);  1: camera -> packed framebuffer;  2: camera -> per-sample hits
 // Work item = one ray (MODE 0) or one pixel with its spp samples (MODE 1/2).
 // ------------------------------------------------------------------------------------------
-template <int MODE, bool COUNTED>
+// WALK > 0: the node phase takes exactly WALK steps between two votes and always votes (the shipped setting,
+// unrolled); WALK == 0: both come from the launch arguments (tuning / tests).
+template <int MODE, bool COUNTED, int WALK>
 __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(TraceArgs a) {
     // per-axis ray constants (origin, 1/dir), one row of 3 float2 per thread: 24-byte stride keeps a
     // half-warp's 64-bit accesses on distinct banks when the lanes agree on the axis
@@ -122,9 +124,9 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
     uint4 stack[STACK_DEPTH];
     int sp = 0;
     const uint32_t root_ref = BIH_REF_NODE(0, a.hdr->root_axis);
-    const bool vote = a.vote_wait != 0;
+    const bool vote = WALK > 0 || a.vote_wait != 0;
     int thresh = a.refill_threshold;          // lanes that must be idle before a partial refill (warp-uniform)
-    const int steps_per_vote = a.vote_walk > 0 ? a.vote_walk : 1;
+    const int steps_per_vote = WALK > 0 ? WALK : (a.vote_walk > 0 ? a.vote_walk : 1);
     const uint32_t ray_smem = (uint32_t)__cvta_generic_to_shared(my_ray);
 
     for (;;) {
@@ -288,7 +290,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
                     // Nu == 1: no internal node; the single leaf starts at slot 0 (and must not be
                     // interval-pruned: the reference tests it unconditionally once the box is hit)
                     if (nu == 1) { cur = BIH_REF_LEAFREF(0); pMin = -FLT_MAX; pMax = FLT_MAX; }
-                    else cur = root_ref;
+                    else if (pMin <= pMax) cur = root_ref;          // box behind the origin: nothing to walk
                 }
             }
             if (MODE == 0) {
@@ -304,51 +306,58 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
         // nobody has a node left, or as soon as the waiting lanes outnumber the walking ones: finishing
         // the node phase for a few stragglers with most lanes idle costs more than testing the held
         // leaves first.
+        // Invariant: an item held in `cur` has a non-empty tight interval that ends at or before the closest hit
+        // (pMin <= pMax <= h.t).  Children inherit it from the tests that select them, so only items that
+        // come off the stack -- h.t may have shrunk since they were pushed -- are checked (POP_VALID); an
+        // item that fails is dropped without a node fetch.  Same visits, same order, same counters as the
+        // entry check of oracle/bih_oracle.c:traverse_proper.
+#define POP_VALID()                                                                                         \
+        do {                                                                                                \
+            cur = NONE;                                                                                     \
+            while (sp > 0) {                                                                                \
+                sp--;                                                                                       \
+                const uint4 e = stack[sp];                                                                  \
+                const float m = fminf(__uint_as_float(e.w), h.t);                                           \
+                if (__uint_as_float(e.z) <= m) { cur = e.x; rMin = __uint_as_float(e.y); pMin = __uint_as_float(e.z); pMax = m; break; } \
+            }                                                                                               \
+        } while (0)
         for (;;) {
-#pragma unroll 1
+#pragma unroll (WALK > 0 ? WALK : 1)
             for (int rep = 0; rep < steps_per_vote && (int)cur >= 0; rep++) {
-                bool popit = true;
-                if (pMin <= fminf(pMax, h.t)) {                        // entry check (closed interval)
-                    // (origin, 1/dir) on this node's axis: one 64-bit LDS at ray_smem + axis * 8
-                    float2 oi;
-                    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(oi.x), "=f"(oi.y) : "r"(ray_smem + ((cur & 3u) << 3)));
-                    // node byte offset = (ref & ~3) * 4, as one 32x32->64 multiply-add on the base pointer
-                    const float4* np;
-                    asm("mad.wide.u32 %0, %1, 4, %2;" : "=l"(np) : "r"(cur & ~3u), "l"(nodes_b));
-                    const float4 nd = __ldg(np);
-                    if (COUNTED) nnodes++;
-                    const uint32_t rl = __float_as_uint(nd.z), rr = __float_as_uint(nd.w);
-                    const bool neg = oi.y < 0.f;                           // near = sign[axis], :286
-                    const float t0 = __fmul_rn(__fsub_rn(nd.x, oi.x), oi.y);   // :288-289
-                    const float t1 = __fmul_rn(__fsub_rn(nd.y, oi.x), oi.y);
-                    const float tn = neg ? t1 : t0, tf = neg ? t0 : t1;
-                    const uint32_t refn = neg ? rr : rl, reff = neg ? rl : rr;
-                    const float nMax = fminf(pMax, tn);
-                    const float fMin = fmaxf(pMin, tf);
-                    const bool go_near = (rMin < tn) && (pMin <= nMax);   // reference's strict test (:292) + closed tight interval
-                    const bool go_far = (fMin <= pMax);
-                    if (go_near && go_far) {
-                        // near before far, except a far LEAF next to a near NODE is tested first (:344-349)
-                        if ((int)refn >= 0 && (int)reff < 0) {
-                            stack[sp] = make_uint4(refn, __float_as_uint(rMin), __float_as_uint(pMin), __float_as_uint(nMax));
-                            cur = reff; rMin = tf; pMin = fMin;
-                        } else {
-                            stack[sp] = make_uint4(reff, __float_as_uint(tf), __float_as_uint(fMin), __float_as_uint(pMax));
-                            cur = refn; pMax = nMax;
-                        }
-                        sp++;
-                        if (COUNTED) maxsp = max(maxsp, (uint32_t)sp);
-                        popit = false;
-                    } else if (go_near) { cur = refn; pMax = nMax; popit = false; }
-                    else if (go_far) { cur = reff; rMin = tf; pMin = fMin; popit = false; }
-                }
-                if (popit) {
-                    if (sp > 0) {
-                        sp--;
-                        const uint4 e = stack[sp];
-                        cur = e.x; rMin = __uint_as_float(e.y); pMin = __uint_as_float(e.z); pMax = __uint_as_float(e.w);
-                    } else cur = NONE;
-                }
+                // (origin, 1/dir) on this node's axis: one 64-bit LDS at ray_smem + axis * 8
+                float2 oi;
+                uint32_t ra;
+                asm("mad.lo.u32 %0, %1, 8, %2;" : "=r"(ra) : "r"(cur & 3u), "r"(ray_smem));
+                asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(oi.x), "=f"(oi.y) : "r"(ra));
+                // node address = base + index * 16, as one 32x32->64 multiply-add on the base pointer
+                const float4* np;
+                asm("mad.wide.u32 %0, %1, 16, %2;" : "=l"(np) : "r"(cur >> 2), "l"(nodes_b));
+                const float4 nd = __ldg(np);
+                if (COUNTED) nnodes++;
+                const uint32_t rl = __float_as_uint(nd.z), rr = __float_as_uint(nd.w);
+                const bool neg = oi.y < 0.f;                           // near = sign[axis], :286
+                const float t0 = __fmul_rn(__fsub_rn(nd.x, oi.x), oi.y);   // :288-289
+                const float t1 = __fmul_rn(__fsub_rn(nd.y, oi.x), oi.y);
+                const float tn = neg ? t1 : t0, tf = neg ? t0 : t1;
+                const uint32_t refn = neg ? rr : rl, reff = neg ? rl : rr;
+                const float nMax = fminf(pMax, tn);
+                const float fMin = fmaxf(pMin, tf);
+                const bool go_near = (rMin < tn) && (pMin <= nMax);   // reference's strict test (:292) + closed tight interval
+                const bool go_far = (fMin <= pMax);
+                if (go_near && go_far) {
+                    // near before far, except a far LEAF next to a near NODE is tested first (:344-349)
+                    if ((int)refn >= 0 && (int)reff < 0) {
+                        stack[sp] = make_uint4(refn, __float_as_uint(rMin), __float_as_uint(pMin), __float_as_uint(nMax));
+                        cur = reff; rMin = tf; pMin = fMin;
+                    } else {
+                        stack[sp] = make_uint4(reff, __float_as_uint(tf), __float_as_uint(fMin), __float_as_uint(pMax));
+                        cur = refn; pMax = nMax;
+                    }
+                    sp++;
+                    if (COUNTED) maxsp = max(maxsp, (uint32_t)sp);
+                } else if (go_near) { cur = refn; pMax = nMax; }
+                else if (go_far) { cur = reff; rMin = tf; pMin = fMin; }
+                else POP_VALID();
             }
             const uint32_t m_walk = __ballot_sync(FULL, (int)cur >= 0);
             if (m_walk == 0) break;
@@ -359,17 +368,12 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
         }
         // ================= phase 2: the leaf this lane holds ===========================================
         if (cur + 1u > 0x80000000u) {
-            if (pMin <= fminf(pMax, h.t)) {
-                const char* tp;
-                asm("mad.wide.u32 %0, %1, 12, %2;" : "=l"(tp) : "r"(cur & 0x7FFFFFFCu), "l"(tris_b));
-                test_leaf<COUNTED>(tp, ox, oy, oz, dx, dy, dz, h, ntris);
-            }
-            if (sp > 0) {
-                sp--;
-                const uint4 e = stack[sp];
-                cur = e.x; rMin = __uint_as_float(e.y); pMin = __uint_as_float(e.z); pMax = __uint_as_float(e.w);
-            } else cur = NONE;
+            const char* tp;
+            asm("mad.wide.u32 %0, %1, 12, %2;" : "=l"(tp) : "r"(cur & 0x7FFFFFFCu), "l"(tris_b));
+            test_leaf<COUNTED>(tp, ox, oy, oz, dx, dy, dz, h, ntris);
+            POP_VALID();
         }
+#undef POP_VALID
         __syncwarp();
     }
 
@@ -408,15 +412,16 @@ int bihrt_resolve_launch(bihrt_ctx* c, uint32_t* fb, int npix, int spp) {
     return BIHRT_OK;
 }
 
-template <int MODE, bool COUNTED>
+#define TRACE_WALK 3
+template <int MODE, bool COUNTED, int WALK>
 static int launch(bihrt_ctx* c, const TraceArgs& a) {
     int per_sm = c->opt_trace_blocks_per_sm;
     if (per_sm <= 0) {
-        BIHRT_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<MODE, COUNTED>, TRACE_THREADS, 0));
+        BIHRT_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<MODE, COUNTED, WALK>, TRACE_THREADS, 0));
         if (per_sm < 1) per_sm = 1;
     }
     BIHRT_CUDA(c, cudaMemsetAsync(a.work, 0, 4 * 1024, c->stream));
-    k_trace<MODE, COUNTED><<<c->sm_count * per_sm, TRACE_THREADS, 0, c->stream>>>(a);
+    k_trace<MODE, COUNTED, WALK><<<c->sm_count * per_sm, TRACE_THREADS, 0, c->stream>>>(a);
     c->kernel_launches += 1;
     BIHRT_CUDA(c, cudaGetLastError());
     return BIHRT_OK;
@@ -431,13 +436,14 @@ int bihrt_trace_launch(bihrt_ctx* c, const TraceArgs& a_in, int mode, bool count
     // its own and the queues only add stealing overhead (-5 % at 4K x 16 spp)
     const bool on = a.queues < 0 ? (rays >= (16ll << 20) && (mode == 0 || a.gshift == 0)) : a.queues != 0;
     a.queues = on ? (c->sm_count < 1024 ? c->sm_count : 1024) : 1;
+    const bool shipped = a.vote_wait != 0 && a.vote_walk == TRACE_WALK;    // the unrolled instantiation
     switch (mode * 2 + (counted ? 1 : 0)) {
-        case 0: return launch<0, false>(c, a);
-        case 1: return launch<0, true>(c, a);
-        case 2: return launch<1, false>(c, a);
-        case 3: return launch<1, true>(c, a);
-        case 4: return launch<2, false>(c, a);
-        case 5: return launch<2, true>(c, a);
+        case 0: return shipped ? launch<0, false, TRACE_WALK>(c, a) : launch<0, false, 0>(c, a);
+        case 1: return launch<0, true, 0>(c, a);
+        case 2: return shipped ? launch<1, false, TRACE_WALK>(c, a) : launch<1, false, 0>(c, a);
+        case 3: return launch<1, true, 0>(c, a);
+        case 4: return shipped ? launch<2, false, TRACE_WALK>(c, a) : launch<2, false, 0>(c, a);
+        case 5: return launch<2, true, 0>(c, a);
     }
     return bihrt_fail(c, BIHRT_ERR_INVALID, "bad trace mode %d", mode);
 }
