@@ -198,9 +198,24 @@ def run_ours(args, rank, world, local_rank):
 
     # N > 1: unit interleave (every rank walks every tile and owns every N-th 32-ray unit of it: balanced, and a
     # pixel keeps all its samples in consecutive lanes); samples / tiles per rank are the fall-backs
-    mode = os.environ.get("BIHRT_BENCH_SHARD", "interleave") if world > 1 else "single"
-    if mode == "interleave" and (32 * (spp & -spp if spp & -spp < 32 else 32)) % world != 0:
+    mode = os.environ.get("BIHRT_BENCH_SHARD", "p2p") if world > 1 else "single"
+    if mode in ("p2p", "interleave") and (32 * (spp & -spp if spp & -spp < 32 else 32)) % world != 0:
         mode = "samples"
+    # p2p = unit interleave with the gather fused into the trace kernel: every rank stores its finished pixels
+    # straight into rank 0's framebuffer (CUDA IPC mapping, NVLink); a one-element all-reduce closes the frame
+    peer_ptr, peer_opened, token = None, False, None
+    if mode == "p2p":
+        try:
+            with torch.cuda.stream(stream):
+                peer_ptr, peer_opened = multi.open_peer_framebuffer(r, dist, W, H, dst=0, device=dev)
+                token = torch.zeros(1, dtype=torch.int32, device=dev)
+        except Exception as ex:       # noqa  (no peer mapping on this box: NCCL reduce instead)
+            log("rank %d: peer framebuffer unavailable (%r); using interleave + reduce" % (rank, ex))
+            peer_ptr = None
+        ok = torch.tensor([1 if peer_ptr else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            mode = "interleave"
     if mode == "samples" and spp < world:
         mode = "tiles"
     by_sample = mode in ("samples", "interleave")        # per-pixel hit counts, resolved after the reduce
@@ -209,6 +224,8 @@ def run_ours(args, rank, world, local_rank):
     def render_my_share():
         if world == 1:
             r.render(cam, W, H, spp=spp, seed=1984, jitter=True)
+        elif mode == "p2p":
+            r.render_interleaved_to(cam, W, H, spp, rank, world, target_ptr=peer_ptr, seed=1984, jitter=True)
         elif mode == "interleave":
             r.render_interleaved(cam, W, H, spp, rank, world, seed=1984, jitter=True)
         elif mode == "samples":
@@ -219,7 +236,9 @@ def run_ours(args, rank, world, local_rank):
     def step():
         nonlocal fb_t
         render_my_share()
-        if world > 1:
+        if mode == "p2p":
+            multi.frame_barrier(dist, token)
+        elif world > 1:
             if fb_t is None:
                 fb_t = multi.framebuffer_tensor(r)
             multi.gather_framebuffer(fb_t, dist, dst=0)
@@ -268,8 +287,12 @@ def run_ours(args, rank, world, local_rank):
     breakdown = None
     if world > 1:
         t_r = max_over_ranks(timed_loop(render_my_share, 3)) / 3
-        t_g = max_over_ranks(timed_loop(lambda: multi.gather_framebuffer(fb_t, dist, dst=0), 3)) / 3
-        breakdown = {"render_shard_ms_max_over_ranks": t_r, "framebuffer_reduce_ms": t_g}
+        if mode == "p2p":
+            t_g = max_over_ranks(timed_loop(lambda: multi.frame_barrier(dist, token), 3)) / 3
+            breakdown = {"render_shard_ms_max_over_ranks": t_r, "frame_barrier_ms": t_g}
+        else:
+            t_g = max_over_ranks(timed_loop(lambda: multi.gather_framebuffer(fb_t, dist, dst=0), 3)) / 3
+            breakdown = {"render_shard_ms_max_over_ranks": t_r, "framebuffer_reduce_ms": t_g}
         barrier()
 
     # ---- N > 1: the gathered frame must be bit-identical to the single-GPU render ------------------
@@ -341,14 +364,16 @@ def run_ours(args, rank, world, local_rank):
                "config": {"workload": name, "triangles": n_tri, "leaves": info["nu"], "rays_per_step": rays_total,
                           "l2": "flushed before every timed step (256 MiB write)", "parallelism": "%s%d" % (mode, world),
                           "sharding": {"single": "one GPU",
+                                       "p2p": "every rank walks every 32x32 tile and owns every N-th 32-ray unit; the trace kernel stores the finished "
+                                              "pixels straight into rank 0's framebuffer over NVLink (CUDA IPC mapping), one-element all-reduce as frame barrier",
                                        "interleave": "every rank walks every 32x32 tile and owns every N-th 32-ray unit (hit counts, reduce, resolve)",
                                        "samples": "samples of every pixel split over ranks (hit counts, reduce, resolve)",
-                                       "tiles": "32x32-pixel tiles round-robin over ranks"}[mode] + "; BIH broadcast once; framebuffer reduce per step"},
+                                       "tiles": "32x32-pixel tiles round-robin over ranks"}[mode] + "; BIH broadcast once" + ("" if mode in ("single", "p2p") else "; framebuffer reduce per step")},
                "build_ms_per_mtri": build_ms / (n_tri / 1e6), "build_ms": build_ms,
                "e2e": {"value": e2e_val, "unit": "Mrays/s", "h2d_bytes_per_step": n_tri * 36, "d2h_bytes_per_step": W * H * 4,
                        "ms_per_step": ms_e2e,
                        "what": "vertices H2D (pinned) + bihrt_build + %sbihrt_render%s + framebuffer D2H (pinned), per frame" % (
-                           "BIH broadcast + " if world > 1 else "", " + framebuffer reduce" if world > 1 else "")},
+                           "BIH broadcast + " if world > 1 else "", " (peer stores into rank 0) + frame barrier" if mode == "p2p" else (" + framebuffer reduce" if world > 1 else ""))},
                "gpu_launches": int(launches), "clocks": clocks}
         if breakdown:
             out["breakdown"] = breakdown
@@ -421,6 +446,10 @@ def run_ours(args, rank, world, local_rank):
         out["reference_kernels_b200"] = reference_kernels_baseline(args, tri, cam)
     if rank == 0:
         emit(out)
+    if peer_opened:
+        r.framebuffer_ipc_close(peer_ptr)
+    if world > 1:
+        barrier()
     r.close()
     if world > 1:
         dist.destroy_process_group()

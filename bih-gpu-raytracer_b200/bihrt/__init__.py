@@ -65,7 +65,7 @@ ABI_SYMBOLS = [
     "bihrt_version", "bihrt_create", "bihrt_destroy", "bihrt_last_error", "bihrt_set_stream", "bihrt_sync",
     "bihrt_set_option", "bihrt_get_stat", "bihrt_scene_load_triangles", "bihrt_scene_update_vertices", "bihrt_scene_load_obj",
     "bihrt_build", "bihrt_refit", "bihrt_get_build_info", "bihrt_export_reference_view", "bihrt_trace", "bihrt_trace_counted",
-    "bihrt_render", "bihrt_render_counted", "bihrt_render_shard", "bihrt_render_samples", "bihrt_render_interleaved", "bihrt_framebuffer_resolve", "bihrt_render_hits", "bihrt_secondary_rays", "bihrt_framebuffer", "bihrt_framebuffer_read",
+    "bihrt_render", "bihrt_render_counted", "bihrt_render_shard", "bihrt_render_samples", "bihrt_render_interleaved", "bihrt_render_interleaved_to", "bihrt_framebuffer_ipc_export", "bihrt_framebuffer_ipc_open", "bihrt_framebuffer_ipc_close", "bihrt_framebuffer_resolve", "bihrt_render_hits", "bihrt_secondary_rays", "bihrt_framebuffer", "bihrt_framebuffer_read",
     "bihrt_bih_blob_bytes", "bihrt_bih_export", "bihrt_bih_import",
 ]
 
@@ -261,6 +261,30 @@ class Renderer:
                                                        C.c_uint64(seed), C.c_uint32(RENDER_JITTER if jitter else 0),
                                                        C.c_int32(index), C.c_int32(count)))
         return self
+
+    def render_interleaved_to(self, camera, w, h, spp, index, count, target_ptr=None, seed=1984, jitter=True):
+        """Multi-GPU unit interleave fused with the gather: the final colours of this rank's pixels are stored by the
+        trace kernel straight into the framebuffer at `target_ptr` (another GPU's, over NVLink; None = own)."""
+        cam = camera if isinstance(camera, Camera) else Camera.from_array(camera)
+        self._check(self._lib.bihrt_render_interleaved_to(self._ctx, C.byref(cam), C.c_int32(w), C.c_int32(h), C.c_int32(spp),
+                                                          C.c_uint64(seed), C.c_uint32(RENDER_JITTER if jitter else 0),
+                                                          C.c_int32(index), C.c_int32(count), C.c_void_p(target_ptr)))
+        return self
+
+    def framebuffer_ipc_export(self, w, h):
+        """64-byte CUDA IPC handle of this context's w x h framebuffer (allocated if needed)."""
+        buf = C.create_string_buffer(64)
+        self._check(self._lib.bihrt_framebuffer_ipc_export(self._ctx, C.c_int32(w), C.c_int32(h), buf))
+        return buf.raw
+
+    def framebuffer_ipc_open(self, handle):
+        """Map another process's framebuffer; returns the device pointer to pass as target_ptr."""
+        p = C.c_void_p()
+        self._check(self._lib.bihrt_framebuffer_ipc_open(self._ctx, C.c_char_p(bytes(handle)), C.byref(p)))
+        return p.value
+
+    def framebuffer_ipc_close(self, ptr):
+        self._check(self._lib.bihrt_framebuffer_ipc_close(self._ctx, C.c_void_p(ptr)))
 
     def framebuffer_resolve(self, spp):
         self._check(self._lib.bihrt_framebuffer_resolve(self._ctx, C.c_int32(spp)))

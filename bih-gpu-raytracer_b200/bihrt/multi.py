@@ -11,8 +11,11 @@ replicated tree, so the partition is data-parallel:
     pixel and stores per-pixel hit counts, bihrt_render_samples -- every rank walks the whole image, so
     the warps keep the single-GPU coherence; the default when spp >= G) or by TILE (32x32-pixel tiles
     dealt round-robin, tile k -> rank k mod G, other pixels 0, bihrt_render_shard; used when spp < G);
-  * the framebuffer is gathered at the end with ONE reduce (SUM of counts, or of disjoint shards),
-    followed for sample sharding by bihrt_framebuffer_resolve on the destination rank.
+  * the framebuffer is gathered either INSIDE the trace kernel (unit interleave, bihrt_render_interleaved_to: every
+    rank stores the final colour of the pixels it owns straight into the gathering GPU's framebuffer, mapped
+    through CUDA IPC, so the transfer rides NVLink while the kernel runs and only a barrier follows), or, for
+    the sample / tile partitions, with ONE reduce (SUM of counts, or of disjoint shards) followed for sample
+    sharding by bihrt_framebuffer_resolve on the destination rank.
 
 No collective runs during traversal.  The helpers take any torch.distributed backend so the same code
 is exercised with gloo on CPU tensors in tests/test_distributed.py.
@@ -71,6 +74,28 @@ def replicate_bih(renderer, dist, src=0, device=None):
         renderer.bih_import(blob, nbytes)
         renderer.sync()
     return nbytes
+
+
+def open_peer_framebuffer(renderer, dist, w, h, dst=0, device=None):
+    """Fused gather: rank `dst` shares its w x h framebuffer with the other ranks (CUDA IPC handle, one 64-byte
+    broadcast); every rank gets the device pointer to hand to Renderer.render_interleaved_to, whose trace kernel
+    then stores the finished pixels straight into rank dst's memory over NVLink.  Returns (pointer, is_peer)."""
+    import torch
+    rank = dist.get_rank()
+    dev = device if device is not None else "cuda:%d" % renderer.device
+    h64 = torch.zeros(64, dtype=torch.uint8, device=dev)
+    if rank == dst:
+        h64.copy_(torch.frombuffer(bytearray(renderer.framebuffer_ipc_export(w, h)), dtype=torch.uint8))
+    dist.broadcast(h64, src=dst)
+    if rank == dst:
+        return renderer.framebuffer_ptr()[0], False
+    return renderer.framebuffer_ipc_open(bytes(h64.cpu().numpy().tobytes())), True
+
+
+def frame_barrier(dist, token):
+    """The fused gather has no data collective: the frame on rank dst is complete when every rank's launch has
+    finished.  A one-element all-reduce on the launching stream orders that (token: 1-element CUDA tensor)."""
+    dist.all_reduce(token)
 
 
 def gather_framebuffer(fb, dist, dst=0):

@@ -166,6 +166,7 @@ int bihrt_set_option(bihrt_ctx* c, const char* name, int64_t v) {
     }
     else if (!strcmp(name, "trace_lane_groups")) c->opt_lane_groups = (int)v;
     else if (!strcmp(name, "trace_sm_queues")) c->opt_sm_queues = (int)v;
+    else if (!strcmp(name, "interleave_chunk")) c->opt_interleave_chunk = (int)std::max<int64_t>(1, std::min<int64_t>(1024, v));
     else if (!strcmp(name, "trace_vote_wait")) c->opt_vote_wait = (int)v;
     else if (!strcmp(name, "trace_vote_walk")) c->opt_vote_walk = (int)v;
     else if (!strcmp(name, "trace_refill_incoherent")) c->opt_refill_incoherent = (int)std::max<int64_t>(1, std::min<int64_t>(32, v));
@@ -480,9 +481,11 @@ static int pick_gshift(bihrt_ctx* c, int nsamples) {
     return g;
 }
 
+// `target` != nullptr: the pixels this launch owns are written there (w*h packed colours, possibly on another GPU)
+// and nothing else is touched: no clearing of the other ranks' pixels, no counts, no resolve.
 static int render_impl(bihrt_ctx* c, const bihrt_camera* cam, int32_t w, int32_t h, int32_t spp, uint64_t seed, uint32_t flags,
                        int32_t shard_index, int32_t shard_count, uint64_t* counters, int32_t s_begin = 0, int32_t s_end = -1,
-                       int32_t il_index = 0, int32_t il_count = 1) {
+                       int32_t il_index = 0, int32_t il_count = 1, uint32_t* target = nullptr) {
     ENTER(c);
     if (s_end < 0) s_end = spp;
     if (s_begin < 0 || s_begin > s_end || s_end > spp) return bihrt_fail(c, BIHRT_ERR_INVALID, "bad sample range [%d,%d) of %d", s_begin, s_end, spp);
@@ -494,28 +497,28 @@ static int render_impl(bihrt_ctx* c, const bihrt_camera* cam, int32_t w, int32_t
     if (shard_count > 1) BIHRT_CUDA(c, cudaMemsetAsync(c->d_fb, 0, px * 4, c->stream));
     TraceArgs a; base_args(c, a);
     a.cam = *cam; a.w = w; a.h = h; a.spp = spp; a.seed = seed; a.flags = flags;
-    a.shard_index = shard_index; a.shard_count = shard_count; a.fb = c->d_fb;
+    a.shard_index = shard_index; a.shard_count = shard_count; a.fb = target ? target : c->d_fb;
     a.s_begin = s_begin; a.s_end = s_end;
     a.gshift = (shard_count > 1) ? 0 : pick_gshift(c, s_end - s_begin);       // tile shards keep "other pixels are 0"
     a.il_index = il_index; a.il_count = il_count;
     if (il_count > 1) {
         if (il_index < 0 || il_index >= il_count || ((32 << a.gshift) % il_count) != 0)
             return bihrt_fail(c, BIHRT_ERR_INVALID, "interleave %d of %d does not divide the %d units of a tile", il_index, il_count, 32 << a.gshift);
-        if (a.gshift == 0) BIHRT_CUDA(c, cudaMemsetAsync(c->d_fb, 0, px * 4, c->stream));   // pixels of the other ranks stay 0
+        // runs of neighbouring units per rank: the largest power of two <= the option that still deals whole runs per tile
+        // (a function of spp and count only, so every rank derives the same pixel ownership)
+        int cs = 0;
+        while ((2 << cs) <= c->opt_interleave_chunk && ((32 << a.gshift) % ((2 << cs) * il_count)) == 0) cs++;
+        a.il_cshift = cs;
     }
-    if (a.gshift > 0) BIHRT_CUDA(c, cudaMemsetAsync(c->d_fb, 0, px * 4, c->stream));   // hit counts are accumulated with atomics
-    if (s_begin == s_end) {            // nothing to trace on this rank: all counts are 0
-        BIHRT_CUDA(c, cudaMemsetAsync(c->d_fb, 0, px * 4, c->stream));
-        return BIHRT_OK;
-    }
-    const bool resolve = a.gshift > 0 && !(flags & BIHRT_RENDER_COUNTS);
-    if (!counters) {
-        if ((rc = bihrt_trace_launch(c, a, 1, false))) return rc;
-        return resolve ? bihrt_resolve_launch(c, c->d_fb, (int)px, s_end - s_begin) : BIHRT_OK;
-    }
+    // Every pixel is written exactly once (colours, or counts when a lane holds all of a pixel's samples) except:
+    // hit counts accumulated with atomics by several lanes, and interleaved launches into the rank's own
+    // framebuffer, where the pixels of the other ranks must read 0 for the reduce.
+    const bool atomics = a.gshift > 0 && (flags & BIHRT_RENDER_COUNTS);
+    if (!target && (atomics || il_count > 1 || s_begin == s_end)) BIHRT_CUDA(c, cudaMemsetAsync(c->d_fb, 0, px * 4, c->stream));
+    if (s_begin == s_end) return BIHRT_OK;            // nothing to trace on this rank: all counts are 0
+    if (!counters) return bihrt_trace_launch(c, a, 1, false);
     BIHRT_CUDA(c, cudaMemsetAsync(c->d_counters, 0, 32, c->stream));
     if ((rc = bihrt_trace_launch(c, a, 1, true))) return rc;
-    if (resolve && (rc = bihrt_resolve_launch(c, c->d_fb, (int)px, s_end - s_begin))) return rc;
     unsigned long long hc[4];
     BIHRT_CUDA(c, cudaMemcpyAsync(hc, c->d_counters, 32, cudaMemcpyDeviceToHost, c->stream));
     BIHRT_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -536,6 +539,67 @@ int bihrt_render_samples(bihrt_ctx* c, const bihrt_camera* cam, int32_t w, int32
 int bihrt_render_interleaved(bihrt_ctx* c, const bihrt_camera* cam, int32_t w, int32_t h, int32_t spp, uint64_t seed, uint32_t flags,
                              int32_t index, int32_t count) {
     return render_impl(c, cam, w, h, spp, seed, flags | BIHRT_RENDER_COUNTS, 0, 1, nullptr, 0, -1, index, count);
+}
+
+// Interleaved render whose owned pixels go, as final colours, straight into `target_fb` (NULL = this context's own
+// framebuffer).  A target on another device of this process gets peer access enabled on first use.
+int bihrt_render_interleaved_to(bihrt_ctx* c, const bihrt_camera* cam, int32_t w, int32_t h, int32_t spp, uint64_t seed, uint32_t flags,
+                                int32_t index, int32_t count, uint32_t* target_fb) {
+    if (!c) return BIHRT_ERR_INVALID;
+    if (flags & BIHRT_RENDER_COUNTS) return bihrt_fail(c, BIHRT_ERR_INVALID, "bihrt_render_interleaved_to writes colours, not counts");
+    if (target_fb) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, target_fb) != cudaSuccess || at.type != cudaMemoryTypeDevice) {
+            cudaGetLastError();
+            return bihrt_fail(c, BIHRT_ERR_INVALID, "target framebuffer is not device memory");
+        }
+        if (at.device != c->device) {
+            cudaSetDevice(c->device);
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, c->device, at.device);
+            if (!can) return bihrt_fail(c, BIHRT_ERR_CUDA, "device %d cannot address the framebuffer on device %d", c->device, at.device);
+            cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return bihrt_fail(c, BIHRT_ERR_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+            cudaGetLastError();
+        }
+    } else {
+        const size_t px = (size_t)(w > 0 ? w : 0) * (size_t)(h > 0 ? h : 0);
+        if (px > c->fb_cap) { int rc = dev_alloc(c, &c->d_fb, px); if (rc) { c->fb_cap = 0; return rc; } c->fb_cap = px; }
+    }
+    return render_impl(c, cam, w, h, spp, seed, flags, 0, 1, nullptr, 0, -1, index, count, target_fb ? target_fb : c->d_fb);
+}
+
+// ---- framebuffer sharing between processes (one process per GPU): CUDA IPC ----------------------------
+int bihrt_framebuffer_ipc_export(bihrt_ctx* c, int32_t w, int32_t h, void* handle64) {
+    ENTER(c);
+    if (!handle64 || w <= 0 || h <= 0) return BIHRT_ERR_INVALID;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle is 64 bytes");
+    const size_t px = (size_t)w * h;
+    if (px > c->fb_cap) { int rc = dev_alloc(c, &c->d_fb, px); if (rc) { c->fb_cap = 0; return rc; } c->fb_cap = px; }
+    c->fb_w = w; c->fb_h = h;
+    cudaIpcMemHandle_t hnd;
+    BIHRT_CUDA(c, cudaIpcGetMemHandle(&hnd, c->d_fb));
+    memcpy(handle64, &hnd, 64);
+    return BIHRT_OK;
+}
+
+int bihrt_framebuffer_ipc_open(bihrt_ctx* c, const void* handle64, uint32_t** peer_fb) {
+    ENTER(c);
+    if (!handle64 || !peer_fb) return BIHRT_ERR_INVALID;
+    cudaIpcMemHandle_t hnd;
+    memcpy(&hnd, handle64, 64);
+    void* p = nullptr;
+    BIHRT_CUDA(c, cudaIpcOpenMemHandle(&p, hnd, cudaIpcMemLazyEnablePeerAccess));
+    *peer_fb = (uint32_t*)p;
+    return BIHRT_OK;
+}
+
+int bihrt_framebuffer_ipc_close(bihrt_ctx* c, uint32_t* peer_fb) {
+    ENTER(c);
+    if (!peer_fb) return BIHRT_OK;
+    BIHRT_CUDA(c, cudaStreamSynchronize(c->stream));
+    BIHRT_CUDA(c, cudaIpcCloseMemHandle(peer_fb));
+    return BIHRT_OK;
 }
 
 int bihrt_framebuffer_resolve(bihrt_ctx* c, int32_t spp) {

@@ -105,6 +105,7 @@ struct bihrt_ctx {
     int opt_chunk_items = 32;
     int opt_vote_wait = 1, opt_vote_walk = 3;
     int opt_lane_groups = -1; // samples of a pixel across lanes: -1 auto (as many as divide the sample count, <= 32), else 2^k
+    int opt_interleave_chunk = 8;  // multi-GPU unit interleave: consecutive units per run (power of two; reduced until it divides a tile)
     int opt_sm_queues = -1; // 1: per-SM work queues (tile locality in L1), 0: one global counter, -1: by launch size
     int64_t kernel_launches = 0;
     int opt_build_graph = 1;            // replay the build as a captured CUDA graph
@@ -130,6 +131,7 @@ struct TraceArgs {
     bihrt_camera cam; int w, h, spp; uint64_t seed; uint32_t flags; int shard_index, shard_count;
     int s_begin, s_end;     // samples [s_begin, s_end) of every pixel are traced by this launch (of spp in total)
     int il_index, il_count; // camera modes, multi-GPU: this launch owns units il_index, il_index + il_count, ... of every tile
+    int il_cshift;          // ... in runs of 2^il_cshift consecutive units (neighbouring pixels), dealt round-robin to the ranks
     int gshift;             // the samples of a pixel are spread over 2^gshift consecutive lanes (camera modes)
     uint32_t* fb;
     unsigned long long* counters; uint32_t* work;

@@ -38,6 +38,17 @@
 
 struct Hit { float t; int slot; };
 
+// Color + rgbToInt, R/src/CUDAKernels.cu:82-88,385-387,420-422: mean over the samples of hit (255,255,0) /
+// miss (20,20,40), packed r | g<<8 | b<<16 (sums of 255/20/40 are exact in binary32)
+__device__ __forceinline__ uint32_t pack_colour(uint32_t hits, int samples) {
+    const float fh = (float)hits, fm = (float)(samples - (int)hits), fs = (float)samples;
+    float cr = __fdiv_rn(__fadd_rn(__fmul_rn(fh, 255.f), __fmul_rn(fm, 20.f)), fs);
+    float cb = __fdiv_rn(__fmul_rn(fm, 40.f), fs);
+    cr = fmaxf(0.f, fminf(255.f, cr));
+    cb = fmaxf(0.f, fminf(255.f, cb));
+    return ((uint32_t)(int)cb << 16) | ((uint32_t)(int)cr << 8) | (uint32_t)(int)cr;
+}
+
 template <bool COUNTED>
 __device__ __forceinline__ void test_leaf(const char* __restrict__ first_tri, float ox, float oy, float oz,
                                           float dx, float dy, float dz, Hit& h, uint32_t& ntris) {
@@ -126,6 +137,10 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
     const uint32_t root_ref = BIH_REF_NODE(0, a.hdr->root_axis);
     const bool vote = WALK > 0 || a.vote_wait != 0;
     int thresh = a.refill_threshold;          // lanes that must be idle before a partial refill (warp-uniform)
+    // colours with a pixel's samples in several lanes: the warp moves from sample to sample in lock step, so the lanes
+    // of a pixel hold its complete hit count when they finish and the pixel is written once, without atomics
+    const bool direct = MODE == 1 && gshift > 0 && !(a.flags & BIHRT_RENDER_COUNTS);
+    if (direct) thresh = 32;
     const int steps_per_vote = WALK > 0 ? WALK : (a.vote_walk > 0 ? a.vote_walk : 1);
     const uint32_t ray_smem = (uint32_t)__cvta_generic_to_shared(my_ray);
 
@@ -155,22 +170,20 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
                     s++;
                     if (s == nsamp) {
                         if (MODE == 1 && gshift > 0) {
-                            // the lanes of one pixel finish together: one atomic per pixel and warp (fb zeroed before, resolved after)
+                            // the lanes of one pixel finish together (always, when the warp moves in lock step)
                             const uint32_t am = __activemask();
                             const uint32_t same = __match_any_sync(am, pixel);
                             const uint32_t sum = __reduce_add_sync(same, hits);
-                            if (sum && lane == __ffs(same) - 1) atomicAdd(&a.fb[pixel], sum);
+                            if (lane == __ffs(same) - 1) {
+                                // colours: the pixel's lanes hold all its samples -> one plain store of the final value
+                                // (a.fb may be another GPU's framebuffer: the store then travels over NVLink);
+                                // counts (a pixel's samples are spread over ranks): one atomic per pixel and warp
+                                if (direct) a.fb[pixel] = pack_colour(sum, nsamp << gshift);
+                                else if (sum) atomicAdd(&a.fb[pixel], sum);
+                            }
                         }
                         else if (MODE == 1 && (a.flags & BIHRT_RENDER_COUNTS)) a.fb[pixel] = hits;     // resolved after the reduce
-                        else if (MODE == 1) {
-                            // Color + rgbToInt, R/src/CUDAKernels.cu:82-88,385-387,420-422 (sums of 255/20/40 are exact)
-                            const float fh = (float)hits, fm = (float)(nsamp - (int)hits), fs = (float)nsamp;
-                            float cr = __fdiv_rn(__fadd_rn(__fmul_rn(fh, 255.f), __fmul_rn(fm, 20.f)), fs);
-                            float cb = __fdiv_rn(__fmul_rn(fm, 40.f), fs);
-                            cr = fmaxf(0.f, fminf(255.f, cr));
-                            cb = fmaxf(0.f, fminf(255.f, cb));
-                            a.fb[pixel] = ((uint32_t)(int)cb << 16) | ((uint32_t)(int)cr << 8) | (uint32_t)(int)cr;
-                        }
+                        else if (MODE == 1) a.fb[pixel] = pack_colour(hits, nsamp);
                         item = ~0ull;
                     }
                 }
@@ -192,11 +205,12 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
                         // unit interleave across GPUs (il_count ranks): this rank owns every il_count-th 32-item unit
                         // of every tile, so all ranks walk all tiles (same locality, perfect balance) and every
                         // pixel keeps all its samples -- and their lane grouping -- on one GPU
-                        const uint32_t ilc = (uint32_t)a.il_count, ili = (uint32_t)a.il_index;
+                        const uint32_t ilc = (uint32_t)a.il_count, ili = (uint32_t)a.il_index, ics = (uint32_t)a.il_cshift;
                         if (a.queues <= 1) {
                             const uint32_t chunk = ilc > 1 ? 32u : (uint32_t)a.chunk_items;
                             const uint64_t fetched = atomicAdd(a.work, chunk); got = chunk;
-                            base = ilc > 1 ? ((fetched >> 5) * ilc + ili) << 5 : fetched;
+                            const uint64_t lu = fetched >> 5;          // this rank's unit -> the frame's unit (runs of 2^il_cshift units)
+                            base = ilc > 1 ? ((((lu >> ics) * ilc + ili) << ics) | (lu & ((1u << ics) - 1u))) << 5 : fetched;
                             if (base >= total) base = ~0ull;
                         } else {
                             const uint32_t tshift = 10 + gshift, ushift = 5 + gshift;       // items / units per tile
@@ -209,7 +223,8 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
                                 if (ld_relaxed(a.work + q) >= units) continue;
                                 const uint32_t u = atomicAdd(a.work + q, 1u);
                                 if (u >= units) continue;
-                                const uint64_t b = (((uint64_t)(u / upt) * a.queues + q) << tshift) + ((uint64_t)((u % upt) * ilc + ili) << 5);
+                                const uint32_t lu = u % upt;
+                                const uint64_t b = (((uint64_t)(u / upt) * a.queues + q) << tshift) + ((uint64_t)((((lu >> ics) * ilc + ili) << ics) | (lu & ((1u << ics) - 1u))) << 5);
                                 if (b < total) { base = b; got = 32; break; }
                             }
                         }
@@ -396,13 +411,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
 __global__ void k_resolve(uint32_t* fb, int npix, int spp) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= npix) return;
-    const uint32_t hits = fb[i];
-    const float fh = (float)hits, fm = (float)(spp - (int)hits), fs = (float)spp;
-    float cr = __fdiv_rn(__fadd_rn(__fmul_rn(fh, 255.f), __fmul_rn(fm, 20.f)), fs);
-    float cb = __fdiv_rn(__fmul_rn(fm, 40.f), fs);
-    cr = fmaxf(0.f, fminf(255.f, cr));
-    cb = fmaxf(0.f, fminf(255.f, cb));
-    fb[i] = ((uint32_t)(int)cb << 16) | ((uint32_t)(int)cr << 8) | (uint32_t)(int)cr;
+    fb[i] = pack_colour(fb[i], spp);
 }
 
 int bihrt_resolve_launch(bihrt_ctx* c, uint32_t* fb, int npix, int spp) {

@@ -166,6 +166,22 @@ BIHRT_API int bihrt_framebuffer_resolve(bihrt_ctx* ctx, int32_t spp);   /* count
  * pixel's samples stay together in consecutive lanes.  count must divide 32 << k, k = log2 of the lane groups. */
 BIHRT_API int bihrt_render_interleaved(bihrt_ctx* ctx, const bihrt_camera* cam, int32_t w, int32_t h, int32_t spp,
                              uint64_t seed, uint32_t flags, int32_t index, int32_t count);
+/* Multi-GPU, unit interleave fused with the framebuffer gather: same partition as bihrt_render_interleaved, but the
+ * final packed colour of every pixel this rank owns is stored by the trace kernel itself straight into `target_fb`
+ * (w*h uint32; NULL = this context's own framebuffer) and no other pixel is touched.  With target_fb = the
+ * framebuffer of the gathering GPU (a device pointer of another context of this process, or one opened with
+ * bihrt_framebuffer_ipc_open in a one-process-per-GPU job) the stores travel over NVLink while the kernel runs:
+ * no per-rank framebuffer clear, no hit-count reduce, no resolve pass.  The frame is complete once every rank's
+ * launch has finished (a barrier, not a data collective).  Requires the lane-group layout every rank uses for
+ * the same spp, so a pixel's samples never leave one rank. */
+BIHRT_API int bihrt_render_interleaved_to(bihrt_ctx* ctx, const bihrt_camera* cam, int32_t w, int32_t h, int32_t spp,
+                                uint64_t seed, uint32_t flags, int32_t index, int32_t count, uint32_t* target_fb);
+/* Sharing the gathering GPU's framebuffer with the other processes of the job (CUDA IPC): export allocates the
+ * context's w x h framebuffer and writes a 64-byte handle; open maps it in another process (peer access over
+ * NVLink) and returns the pointer to pass as target_fb; close unmaps it. */
+BIHRT_API int bihrt_framebuffer_ipc_export(bihrt_ctx* ctx, int32_t w, int32_t h, void* handle64);
+BIHRT_API int bihrt_framebuffer_ipc_open(bihrt_ctx* ctx, const void* handle64, uint32_t** peer_fb);
+BIHRT_API int bihrt_framebuffer_ipc_close(bihrt_ctx* ctx, uint32_t* peer_fb);
 /* Per-sample hit buffers of the same rays bihrt_render traces (index = (j*w+i)*spp + s); device or
  * host outputs, any may be NULL.  Used by the parity tests. */
 BIHRT_API int bihrt_render_hits(bihrt_ctx* ctx, const bihrt_camera* cam, int32_t w, int32_t h, int32_t spp,

@@ -46,4 +46,34 @@ def test_two_gpus_render_the_same_image(scenes):
             multi.framebuffer_tensor(r0).copy_(torch.from_numpy(total.astype(np.int32)).to("cuda:0"))
             torch.cuda.synchronize(0)
             np.testing.assert_array_equal(r0.framebuffer_resolve(spp).framebuffer(), full)
+    # fused gather: device 1's trace kernel stores its pixels straight into device 0's framebuffer (peer access)
+    r0.render(cam, w, h, spp=1); r0.sync()
+    ptr0 = r0.framebuffer_ptr()[0]
+    multi.framebuffer_tensor(r0).zero_()
+    torch.cuda.synchronize(0)
+    r0.render_interleaved_to(cam, w, h, spp, 0, 2, None, jitter=True)
+    r1.render_interleaved_to(cam, w, h, spp, 1, 2, ptr0, jitter=True)
+    r0.sync(); r1.sync()
+    np.testing.assert_array_equal(r0.framebuffer(), full)
     r0.close(); r1.close()
+
+
+@pytest.mark.parametrize("spp,count", [(8, 2), (16, 8), (4, 4), (1, 2), (3, 4), (6, 8)])
+def test_interleaved_to_one_framebuffer_is_the_full_frame(scenes, spp, count):
+    """The fused-gather partition on ONE device: `count` launches, each owning every count-th unit, write final
+    colours into the same framebuffer without clearing it; together they must reproduce bihrt_render exactly."""
+    import torch
+    import bihrt
+    from bihrt import multi
+    tri = scenes.displaced_sphere(96)
+    cam = scenes.pinhole_camera(aspect=333 / 190)
+    w, h = 333, 190                        # ragged: edge tiles with padding pixels
+    r = bihrt.Renderer(0)
+    r.load_models(tri).build()
+    full = r.render(cam, w, h, spp=spp, jitter=True).framebuffer().copy()
+    multi.framebuffer_tensor(r).fill_(0x55555555)
+    torch.cuda.synchronize()
+    for k in range(count):
+        r.render_interleaved_to(cam, w, h, spp, k, count, None, jitter=True)
+    np.testing.assert_array_equal(r.framebuffer(), full)
+    r.close()
