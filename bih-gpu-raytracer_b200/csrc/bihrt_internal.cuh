@@ -94,6 +94,10 @@ struct bihrt_ctx {
     void*     d_io = nullptr; size_t io_cap = 0;      // staging for host ray lists / results
     unsigned long long* d_counters = nullptr;
     uint32_t* d_work = nullptr;                        // persistent-kernel work counter
+    // cost-ordered tiles: the longest unit of every 32x32-pixel tile measured by the previous launch of the same frame
+    // geometry, and the tile order (most expensive first) derived from it
+    uint32_t *d_tile_cost = nullptr, *d_tile_order = nullptr; size_t tile_cap = 0;
+    uint64_t  tile_sig = 0; bool tile_order_valid = false;
 
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool        build_timed = false;
@@ -106,6 +110,7 @@ struct bihrt_ctx {
     int opt_vote_wait = 1, opt_vote_walk = 3;
     int opt_lane_groups = -1; // samples of a pixel across lanes: -1 auto (as many as divide the sample count, <= 32), else 2^k
     int opt_interleave_chunk = 8;  // multi-GPU unit interleave: consecutive units per run (power of two; reduced until it divides a tile)
+    int opt_tile_order = 1; // camera modes: start the tiles that were expensive in the previous frame first (1: launches under 48 M rays, 2: always, 0: never)
     int opt_sm_queues = -1; // 1: per-SM work queues (tile locality in L1), 0: one global counter, -1: by launch size
     int64_t kernel_launches = 0;
     int opt_build_graph = 1;            // replay the build as a captured CUDA graph
@@ -132,6 +137,8 @@ struct TraceArgs {
     int s_begin, s_end;     // samples [s_begin, s_end) of every pixel are traced by this launch (of spp in total)
     int il_index, il_count; // camera modes, multi-GPU: this launch owns units il_index, il_index + il_count, ... of every tile
     int il_cshift;          // ... in runs of 2^il_cshift consecutive units (neighbouring pixels), dealt round-robin to the ranks
+    const uint32_t* tile_order; // camera modes: tile processed m-th (a permutation of this launch's tiles; NULL = in order)
+    uint32_t* tile_cost;        // camera modes: longest unit of every tile, in clock ticks >> 8 (NULL = not recorded)
     int gshift;             // the samples of a pixel are spread over 2^gshift consecutive lanes (camera modes)
     uint32_t* fb;
     unsigned long long* counters; uint32_t* work;
@@ -144,6 +151,7 @@ struct TraceArgs {
 };
 int bihrt_trace_launch(bihrt_ctx* c, const TraceArgs& a, int mode /*0 rays,1 render fb,2 render hits*/, bool counted);
 int bihrt_resolve_launch(bihrt_ctx* c, uint32_t* fb, int npix, int spp);
+int bihrt_tile_order_launch(bihrt_ctx* c, uint32_t ntiles);
 // shade.cu
 int bihrt_secondary_launch(bihrt_ctx* c, const float* t, const int32_t* slot, int64_t n, uint32_t* tile_cnt, unsigned long long* total,
                            const bihrt_camera& cam, int w, int h, int spp, uint64_t seed, uint32_t flags, int kind, const float light[3],

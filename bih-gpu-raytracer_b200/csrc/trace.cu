@@ -121,6 +121,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
     uint32_t my_queue = 0;
     if (a.queues > 1) { asm("mov.u32 %0, %%smid;" : "=r"(my_queue)); my_queue %= (uint32_t)a.queues; }
     uint64_t pool_next = 0, pool_end = 0;      // warp-uniform
+    long long unit_t0 = 0; uint32_t unit_tile = 0xFFFFFFFFu;   // warp-uniform: start time / tile of the packet being traced
     bool exhausted = false;                    // warp-uniform: the global counter ran past `total`
 
     // lane state
@@ -189,6 +190,11 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
                 }
                 want_item = (item == ~0ull);
             }
+            // the packet that just drained: its duration is the cost of its tile for the next frame's order
+            if (MODE != 0 && fresh && a.tile_cost && unit_tile != 0xFFFFFFFFu) {
+                if (lane == 0) atomicMax(a.tile_cost + unit_tile, (uint32_t)min((unsigned long long)(clock64() - unit_t0) >> 8, 0xFFFFFFFFull));
+                unit_tile = 0xFFFFFFFFu;
+            }
             // hand out new items (warp-uniform control flow)
             uint32_t want = __ballot_sync(FULL, want_item);
             if (MODE != 0 && busy != 0) want = 0;                 // pixels: wait for the whole warp
@@ -234,6 +240,11 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
                     if (base == ~0ull) { exhausted = true; break; }
                     pool_next = base;
                     pool_end = min(base + got, total);
+                    if (MODE != 0 && a.tile_cost && unit_tile == 0xFFFFFFFFu) {
+                        const uint32_t m = (uint32_t)(base >> (10 + gshift));
+                        unit_tile = a.tile_order ? __ldg(a.tile_order + m) : m;
+                        unit_t0 = clock64();
+                    }
                 }
                 const uint64_t avail = pool_end - pool_next;
                 const uint32_t rank = __popc(want & lt);
@@ -243,7 +254,8 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
                     if (MODE != 0) {
                         const uint64_t pix = item >> gshift;
                         s0 = a.s_begin + (int)((uint32_t)item & ((1u << gshift) - 1u)) * nsamp;
-                        const uint32_t m = (uint32_t)(pix >> 10), q = (uint32_t)pix & 1023u;
+                        const uint32_t mi = (uint32_t)(pix >> 10), q = (uint32_t)pix & 1023u;
+                        const uint32_t m = a.tile_order ? __ldg(a.tile_order + mi) : mi;      // m-th tile in cost order
                         const int tile = a.shard_index + (int)m * a.shard_count;
                         const int px = (tile % tx) * 32 + (int)((q >> 5) & 3u) * 8 + (int)(q & 7u);
                         const int py = (tile / tx) * 32 + (int)(q >> 7) * 4 + (int)((q >> 3) & 3u);
@@ -414,6 +426,76 @@ __global__ void k_resolve(uint32_t* fb, int npix, int spp) {
     fb[i] = pack_colour(fb[i], spp);
 }
 
+// Tile order for the next launch of the same frame geometry, from the costs the launch that just ended measured
+// (longest 32-ray unit of each tile).  Tiles are put in TILE_CLASSES classes by cost relative to the frame's longest
+// unit (>= 1/2, >= 1/4, >= 1/8, >= 1/16, the rest), most expensive class first, scan order kept inside a class (a
+// stable partition: the bulk of the frame is still traced in scan order and neighbouring tiles share L1 / L2).
+// A unit on the silhouette of the 1 M-triangle sphere is ~0.4 ms of dependent fetches; started last it is the tail
+// of the launch, started first it overlaps everything else.
+#define TILE_CLASSES 5
+__device__ __forceinline__ int tile_class(uint32_t c, uint32_t mx) {
+    int k = 0;
+#pragma unroll
+    for (int j = 1; j < TILE_CLASSES; j++) k += c < max(1u, mx >> j);
+    return k;
+}
+__global__ void __launch_bounds__(1024) k_tile_order(uint32_t* __restrict__ cost, uint32_t* __restrict__ order, uint32_t ntiles) {
+    __shared__ uint32_t s_w[TILE_CLASSES][32];
+    __shared__ uint32_t s_max, s_base[TILE_CLASSES];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t per = (ntiles + 1023u) / 1024u, i0 = min(ntiles, threadIdx.x * per), i1 = min(ntiles, i0 + per);
+    uint32_t mx = 0;
+    for (uint32_t i = i0; i < i1; i++) mx = max(mx, cost[i]);
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    if (lane == 0) s_w[0][w] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) { uint32_t m = 0; for (int k = 0; k < 32; k++) m = max(m, s_w[0][k]); s_max = m; }
+    __syncthreads();
+    mx = s_max;
+    uint32_t cnt[TILE_CLASSES], inc[TILE_CLASSES];
+#pragma unroll
+    for (int k = 0; k < TILE_CLASSES; k++) cnt[k] = 0;
+    for (uint32_t i = i0; i < i1; i++) {
+        const int cl = tile_class(cost[i], mx);
+#pragma unroll
+        for (int k = 0; k < TILE_CLASSES; k++) cnt[k] += (cl == k);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < TILE_CLASSES; k++) {                      // block-wide exclusive scan of every class count
+        inc[k] = cnt[k];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc[k], o); if (lane >= o) inc[k] += t; }
+        if (lane == 31) s_w[k][w] = inc[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < TILE_CLASSES) {
+        uint32_t run = 0;
+        for (int j = 0; j < 32; j++) { const uint32_t x = s_w[threadIdx.x][j]; s_w[threadIdx.x][j] = run; run += x; }
+        s_base[threadIdx.x] = run;                                // class total
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { uint32_t run = 0; for (int k = 0; k < TILE_CLASSES; k++) { const uint32_t x = s_base[k]; s_base[k] = run; run += x; } }
+    __syncthreads();
+    uint32_t pos[TILE_CLASSES];
+#pragma unroll
+    for (int k = 0; k < TILE_CLASSES; k++) pos[k] = s_base[k] + s_w[k][w] + inc[k] - cnt[k];
+    for (uint32_t i = i0; i < i1; i++) {
+        const int cl = tile_class(cost[i], mx);
+#pragma unroll
+        for (int k = 0; k < TILE_CLASSES; k++) if (cl == k) order[pos[k]++] = i;
+    }
+    __syncthreads();
+    for (uint32_t i = i0; i < i1; i++) cost[i] = 0;
+}
+
+int bihrt_tile_order_launch(bihrt_ctx* c, uint32_t ntiles) {
+    k_tile_order<<<1, 1024, 0, c->stream>>>(c->d_tile_cost, c->d_tile_order, ntiles);
+    c->kernel_launches += 1;
+    BIHRT_CUDA(c, cudaGetLastError());
+    return BIHRT_OK;
+}
+
 int bihrt_resolve_launch(bihrt_ctx* c, uint32_t* fb, int npix, int spp) {
     k_resolve<<<(npix + 255) / 256, 256, 0, c->stream>>>(fb, npix, spp);
     c->kernel_launches += 1;
@@ -445,14 +527,46 @@ int bihrt_trace_launch(bihrt_ctx* c, const TraceArgs& a_in, int mode, bool count
     // its own and the queues only add stealing overhead (-5 % at 4K x 16 spp)
     const bool on = a.queues < 0 ? (rays >= (16ll << 20) && (mode == 0 || a.gshift == 0)) : a.queues != 0;
     a.queues = on ? (c->sm_count < 1024 ? c->sm_count : 1024) : 1;
-    const bool shipped = a.vote_wait != 0 && a.vote_walk == TRACE_WALK;    // the unrolled instantiation
-    switch (mode * 2 + (counted ? 1 : 0)) {
-        case 0: return shipped ? launch<0, false, TRACE_WALK>(c, a) : launch<0, false, 0>(c, a);
-        case 1: return launch<0, true, 0>(c, a);
-        case 2: return shipped ? launch<1, false, TRACE_WALK>(c, a) : launch<1, false, 0>(c, a);
-        case 3: return launch<1, true, 0>(c, a);
-        case 4: return shipped ? launch<2, false, TRACE_WALK>(c, a) : launch<2, false, 0>(c, a);
-        case 5: return launch<2, true, 0>(c, a);
+    // cost-ordered tiles (camera modes, one global counter): reuse the order measured by the previous launch of the same
+    // frame geometry; always record the costs of this one
+    uint32_t ntiles = 0;
+    // (launches of tens of milliseconds have no tail to speak of and lose ~0.5 % to the changed tile neighbourhood)
+    if (mode != 0 && a.queues == 1 && (c->opt_tile_order > 1 || (c->opt_tile_order == 1 && rays < (48ll << 20)))) {
+        const int tx = (a.w + 31) / 32, ty = (a.h + 31) / 32, T = tx * ty;
+        const int mine = T > a.shard_index ? (T - a.shard_index + a.shard_count - 1) / a.shard_count : 0;
+        if (mine > 1 && mine <= 65536) {
+            ntiles = (uint32_t)mine;
+            if ((size_t)ntiles > c->tile_cap) {
+                if (c->d_tile_cost) cudaFree(c->d_tile_cost);
+                if (c->d_tile_order) cudaFree(c->d_tile_order);
+                c->d_tile_cost = c->d_tile_order = nullptr; c->tile_cap = 0; c->tile_order_valid = false;
+                if (cudaMalloc(&c->d_tile_cost, (size_t)ntiles * 4) != cudaSuccess || cudaMalloc(&c->d_tile_order, (size_t)ntiles * 4) != cudaSuccess) {
+                    cudaGetLastError(); ntiles = 0;
+                } else c->tile_cap = ntiles;
+            }
+        }
+        if (ntiles) {
+            const uint64_t sig = ((uint64_t)a.w << 48) ^ ((uint64_t)a.h << 32) ^ ((uint64_t)a.gshift << 28) ^ ((uint64_t)a.shard_index << 20) ^
+                                 ((uint64_t)a.shard_count << 12) ^ ((uint64_t)a.il_index << 6) ^ (uint64_t)a.il_count ^ ((uint64_t)(a.s_end - a.s_begin) << 56);
+            if (sig != c->tile_sig) { c->tile_sig = sig; c->tile_order_valid = false; }
+            if (!c->tile_order_valid) BIHRT_CUDA(c, cudaMemsetAsync(c->d_tile_cost, 0, (size_t)ntiles * 4, c->stream));
+            a.tile_cost = c->d_tile_cost;
+            a.tile_order = c->tile_order_valid ? c->d_tile_order : nullptr;
+        }
     }
-    return bihrt_fail(c, BIHRT_ERR_INVALID, "bad trace mode %d", mode);
+    const bool shipped = a.vote_wait != 0 && a.vote_walk == TRACE_WALK;    // the unrolled instantiation
+    int rc = BIHRT_ERR_INVALID;
+    switch (mode * 2 + (counted ? 1 : 0)) {
+        case 0: rc = shipped ? launch<0, false, TRACE_WALK>(c, a) : launch<0, false, 0>(c, a); break;
+        case 1: rc = launch<0, true, 0>(c, a); break;
+        case 2: rc = shipped ? launch<1, false, TRACE_WALK>(c, a) : launch<1, false, 0>(c, a); break;
+        case 3: rc = launch<1, true, 0>(c, a); break;
+        case 4: rc = shipped ? launch<2, false, TRACE_WALK>(c, a) : launch<2, false, 0>(c, a); break;
+        case 5: rc = launch<2, true, 0>(c, a); break;
+        default: return bihrt_fail(c, BIHRT_ERR_INVALID, "bad trace mode %d", mode);
+    }
+    if (rc == BIHRT_OK && ntiles) {
+        if ((rc = bihrt_tile_order_launch(c, ntiles)) == BIHRT_OK) c->tile_order_valid = true;
+    }
+    return rc;
 }

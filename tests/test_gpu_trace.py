@@ -214,6 +214,31 @@ def test_scheduling_variants_do_not_change_results(renderer, scenes, oracle, opt
         np.testing.assert_array_equal(tt, t1)
 
 
+@pytest.mark.parametrize("spp", [1, 4, 3])
+def test_cost_ordered_tiles_do_not_change_the_frame(scenes, oracle, spp):
+    """The second and later launches of a frame geometry trace the tiles in the cost order the previous launch
+    measured (expensive tiles first).  Pixels, per-sample hits and the framebuffer must not depend on that order."""
+    import bihrt
+    tri = scenes.displaced_sphere(160)
+    cam = scenes.pinhole_camera(aspect=331 / 197)
+    w, h = 331, 197                                   # ragged edge tiles
+    ob = oracle.Bih(tri)
+    rays = oracle.camera_rays(cam, w, h, spp=spp, jitter=True)
+    t0, s0, _ = ob.trace(rays, "ref")
+    fb0 = oracle.pack_framebuffer(s0, w, h, spp)
+    r = bihrt.Renderer(0)
+    r.load_models(tri).build()
+    for order in (2, 1, 0):                           # always / small launches / never
+        r.set_option("trace_tile_order", order)
+        for rep in range(3):                          # launch 0 has no history, 1 and 2 follow the measured costs
+            fb = r.render(cam, w, h, spp=spp, jitter=True).framebuffer()
+            np.testing.assert_array_equal(fb.ravel(), fb0)
+            tt, ss, _ = r.render_hits(cam, w, h, spp=spp, jitter=True)
+            np.testing.assert_array_equal(ss, s0)
+            np.testing.assert_array_equal(tt, t0)
+    r.close()
+
+
 def test_axis_parallel_and_degenerate_rays(renderer, scenes, oracle):
     """Rays with zero direction components (1/0 = inf, 0*inf = NaN plane distances), origins inside the scene,
     on the scene box, and pointing away: the kernel must follow the oracle's IEEE behaviour exactly."""

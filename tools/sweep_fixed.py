@@ -19,11 +19,16 @@ def timed(fn, do_flush, reps=7):
             e0.record(st); fn(); e1.record(st)
         torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
     return min(ts)
-for spp in (1, 16):
-    for (w, h) in ((3840, 2160), (1920, 1080), (960, 540), (480, 270), (240, 135)):
+import sys as _s
+for oset in (_s.argv[1] if len(_s.argv) > 1 else "").split(";"):
+  for kv in filter(None, oset.split(",")):
+      r.set_option(kv.split("=")[0], int(kv.split("=")[1]))
+  print("options:", oset or "(default)")
+  for spp in (1, 16):
+    for (w, h) in ( (1920, 1080), (960, 540), (480, 270), (240, 135)):
         cam = scenes.pinhole_camera(aspect=w / h)
         fn = lambda: r.render(cam, w, h, spp=spp, jitter=spp > 1)
         fn(); r.sync()
         a, b = timed(fn, True), timed(fn, False)
         n = w * h * spp
-        print("spp %2d %4dx%4d rays %9d: flushed %.3f ms (%.0f Mr/s)  warm %.3f ms (%.0f Mr/s)" % (spp, w, h, n, a, n / a / 1e3, b, n / b / 1e3), flush=True)
+        print("  " + "spp %2d %4dx%4d rays %9d: flushed %.3f ms (%.0f Mr/s)  warm %.3f ms (%.0f Mr/s)" % (spp, w, h, n, a, n / a / 1e3, b, n / b / 1e3), flush=True)
