@@ -153,8 +153,8 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
         // threshold too).  Lanes that have nothing left park until then.
         const uint32_t idle = __ballot_sync(FULL, cur == NONE);
         const uint32_t busy = ~idle;
-        const uint32_t can = __ballot_sync(FULL, cur == NONE && (tracing || item != ~0ull || MODE == 0));
-        if (idle && (busy == 0 || __popc(can) >= thresh)) {
+        // (the count of lanes that could go on is only needed for a partial refill; every term before it is warp-uniform)
+        if (idle && (busy == 0 || (thresh < 32 && __popc(__ballot_sync(FULL, cur == NONE && (tracing || item != ~0ull || MODE == 0))) >= thresh))) {
             const bool fresh = (busy == 0);          // the warp starts a new packet together
             int new_thresh = -1;
             bool want_item = false;
