@@ -8,10 +8,12 @@ Workload (config.workload): the 1 002 528-triangle displaced sphere of BASELINE 
 the north star's 70 % target is quoted on) seen by the config-2 camera, traced with config 4's ray
 load: 3840x2160 pixels x 16 jittered primary rays = 132 710 400 rays per step.  A step = one frame's
 trace with the BIH resident in HBM.  At N > 1 the frame's rays are partitioned over the ranks (strong
-scaling: total work fixed) -- by unit interleave (every rank walks every tile and owns every N-th 32-ray
-unit, i.e. a few neighbouring pixels with all their samples) -- the
-BIH built on rank 0 is replicated by one NCCL broadcast before the timed region, and every step ends
-with the framebuffer reduce to rank 0 (+ resolve of the hit counts to packed colours).
+scaling: total work fixed) by unit interleave (every rank walks every tile and owns every N-th run of
+32-ray units, i.e. a few neighbouring pixels with all their samples); the BIH built on rank 0 is
+replicated by one NCCL broadcast before the timed region; the gather is fused into the trace kernel:
+every rank stores the final colour of its pixels straight into rank 0's framebuffer (CUDA IPC mapping,
+NVLink) and a one-element all-reduce closes the frame (BIHRT_BENCH_SHARD=interleave|samples|tiles select
+the NCCL-reduce variants instead).
 
 `value`  = rays of the whole frame / max-over-ranks device time (CUDA events on the launching stream).
 `e2e`    = the same metric for the reference's full per-frame sequence through the C ABI with HOST
@@ -363,6 +365,8 @@ def run_ours(args, rank, world, local_rank):
                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                "config": {"workload": name, "triangles": n_tri, "leaves": info["nu"], "rays_per_step": rays_total,
                           "l2": "flushed before every timed step (256 MiB write)", "parallelism": "%s%d" % (mode, world),
+                          "scheduling": "launches under 48 M rays per GPU start the tiles whose longest unit was slow in the previous frame of the "
+                                        "same geometry first (costs measured by the kernel itself; warm-up frames provide the first order)",
                           "sharding": {"single": "one GPU",
                                        "p2p": "every rank walks every 32x32 tile and owns every N-th 32-ray unit; the trace kernel stores the finished "
                                               "pixels straight into rank 0's framebuffer over NVLink (CUDA IPC mapping), one-element all-reduce as frame barrier",

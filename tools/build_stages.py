@@ -9,7 +9,10 @@ NAMES = ["init+memsets", "scene_box", "morton", "sort0", "sort1", "sort2", "sort
 r = bihrt.Renderer(0)
 r.set_option("profile", 1)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-for key in (sys.argv[1:] or ["1m"]):
+OPTS = [a for a in sys.argv[1:] if "=" in a]
+for kv in OPTS:
+    r.set_option(kv.split("=")[0], int(kv.split("=")[1]))
+for key in ([a for a in sys.argv[1:] if "=" not in a] or ["1m"]):
     tri = scenes.displaced_sphere(scenes.SPHERE_NSEG[key])
     r.load_models(torch.from_numpy(tri).cuda())
     acc = []
