@@ -365,7 +365,7 @@ def run_ours(args, rank, world, local_rank):
                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                "config": {"workload": name, "triangles": n_tri, "leaves": info["nu"], "rays_per_step": rays_total,
                           "l2": "flushed before every timed step (256 MiB write)", "parallelism": "%s%d" % (mode, world),
-                          "scheduling": "launches under 48 M rays per GPU start the tiles whose longest unit was slow in the previous frame of the "
+                          "scheduling": "launches of 1 M .. 48 M rays per GPU start the tiles whose longest unit was slow in the previous frame of the "
                                         "same geometry first (costs measured by the kernel itself; warm-up frames provide the first order)",
                           "sharding": {"single": "one GPU",
                                        "p2p": "every rank walks every 32x32 tile and owns every N-th 32-ray unit; the trace kernel stores the finished "
