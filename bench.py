@@ -187,7 +187,7 @@ def run_ours(args, rank, world, local_rank):
         r.sync()
     with torch.cuda.stream(stream):
         if world > 1:
-            multi.replicate_bih(r, dist, src=0, device=dev)
+            multi.replicate_bih_inplace(r, dist, n_tri, src=0)
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
 
     def barrier():
@@ -317,7 +317,7 @@ def run_ours(args, rank, world, local_rank):
             r.update_vertices(pinned_tri)                    # H2D, pinned
             r.build()
         if world > 1:
-            multi.replicate_bih(r, dist, src=0, device=dev)
+            multi.replicate_bih_inplace(r, dist, n_tri, src=0)
         step()
         if rank == 0:
             r.framebuffer(out=host_fb)                       # D2H, pinned; synchronises
@@ -329,6 +329,58 @@ def run_ours(args, rank, world, local_rank):
     ms_e2e = max_over_ranks(timed_loop(e2e_step, e2e_steps)) / e2e_steps
     barrier()
     e2e_val = rays_total / (ms_e2e * 1e-3) / 1e6
+
+    # ---- N > 1: BASELINE config 5 at N GPUs: animated 1 M-triangle scene, rebuild + 1080p x 1 spp trace per frame --------
+    # (a) rank 0 rebuilds and broadcasts the BIH, (b) every rank rebuilds locally (deterministic build => identical
+    # trees, no broadcast); both end with the fused gather into rank 0's framebuffer + frame barrier
+    animated = None
+    if world > 1 and mode == "p2p" and args.scene == "1m":
+        try:
+            aw, ah = 1920, 1080
+            acam = scenes.pinhole_camera(aspect=aw / ah)
+            if rank != 0:
+                r.load_models(torch.from_numpy(scenes.displaced_sphere(nseg)).to(dev))
+                r.build()
+            r.sync()
+            barrier()
+
+            def frame_bcast():
+                if rank == 0:
+                    r.build()
+                multi.replicate_bih_inplace(r, dist, n_tri, src=0)
+                r.render_interleaved_to(acam, aw, ah, 1, rank, world, target_ptr=peer_ptr, seed=1984, jitter=False)
+                multi.frame_barrier(dist, token)
+
+            def frame_local():
+                r.build()
+                r.render_interleaved_to(acam, aw, ah, 1, rank, world, target_ptr=peer_ptr, seed=1984, jitter=False)
+                multi.frame_barrier(dist, token)
+
+            def trace_only():
+                r.render_interleaved_to(acam, aw, ah, 1, rank, world, target_ptr=peer_ptr, seed=1984, jitter=False)
+                multi.frame_barrier(dist, token)
+
+            res = {}
+            for nm, fn in (("frame_ms_bih_broadcast", frame_bcast), ("frame_ms_local_rebuild", frame_local), ("trace_ms", trace_only)):
+                with torch.cuda.stream(stream):
+                    for _ in range(3):
+                        fn()
+                barrier()
+                res[nm] = max_over_ranks(timed_loop(fn, 5)) / 5
+                barrier()
+            # the frame of the local-rebuild variant must equal the single-GPU render
+            with torch.cuda.stream(stream):
+                frame_local()
+            barrier()
+            if rank == 0:
+                mfb = r.framebuffer().copy()
+                sfb = r.render(acam, aw, ah, spp=1, seed=1984, jitter=False).framebuffer()
+                res["image_bit_identical_to_single_gpu"] = bool(np.array_equal(mfb, sfb))
+                res["what"] = "config 5 at %d GPUs: 1 M triangles rebuilt every frame + 1920x1080 x 1 spp primary rays; max over ranks, L2 flushed" % world
+            barrier()
+            animated = res
+        except Exception as ex:       # noqa
+            animated = {"error": repr(ex)[:200]}
 
     out = None
     if rank == 0:
@@ -365,7 +417,7 @@ def run_ours(args, rank, world, local_rank):
                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                "config": {"workload": name, "triangles": n_tri, "leaves": info["nu"], "rays_per_step": rays_total,
                           "l2": "flushed before every timed step (256 MiB write)", "parallelism": "%s%d" % (mode, world),
-                          "scheduling": "launches of 1 M .. 48 M rays per GPU start the tiles whose longest unit was slow in the previous frame of the "
+                          "scheduling": "launches of 64 k .. 48 M rays per GPU (scenes of >= 10 k triangles) start the tiles whose longest unit was slow in the previous frame of the "
                                         "same geometry first (costs measured by the kernel itself; warm-up frames provide the first order)",
                           "sharding": {"single": "one GPU",
                                        "p2p": "every rank walks every 32x32 tile and owns every N-th 32-ray unit; the trace kernel stores the finished "
@@ -377,8 +429,10 @@ def run_ours(args, rank, world, local_rank):
                "e2e": {"value": e2e_val, "unit": "Mrays/s", "h2d_bytes_per_step": n_tri * 36, "d2h_bytes_per_step": W * H * 4,
                        "ms_per_step": ms_e2e,
                        "what": "vertices H2D (pinned) + bihrt_build + %sbihrt_render%s + framebuffer D2H (pinned), per frame" % (
-                           "BIH broadcast + " if world > 1 else "", " (peer stores into rank 0) + frame barrier" if mode == "p2p" else (" + framebuffer reduce" if world > 1 else ""))},
+                           "BIH broadcast (in place, blob to blob) + " if world > 1 else "", " (peer stores into rank 0) + frame barrier" if mode == "p2p" else (" + framebuffer reduce" if world > 1 else ""))},
                "gpu_launches": int(launches), "clocks": clocks}
+        if animated:
+            out["animated_frame_1080p_1spp"] = animated
         if breakdown:
             out["breakdown"] = breakdown
             out["multi_gpu_image_bit_identical_to_single_gpu"] = image_ok

@@ -65,7 +65,7 @@ ABI_SYMBOLS = [
     "bihrt_version", "bihrt_create", "bihrt_destroy", "bihrt_last_error", "bihrt_set_stream", "bihrt_sync",
     "bihrt_set_option", "bihrt_get_stat", "bihrt_scene_load_triangles", "bihrt_scene_update_vertices", "bihrt_scene_load_obj",
     "bihrt_build", "bihrt_refit", "bihrt_get_build_info", "bihrt_export_reference_view", "bihrt_trace", "bihrt_trace_counted",
-    "bihrt_render", "bihrt_render_counted", "bihrt_render_shard", "bihrt_render_samples", "bihrt_render_interleaved", "bihrt_render_interleaved_to", "bihrt_framebuffer_ipc_export", "bihrt_framebuffer_ipc_open", "bihrt_framebuffer_ipc_close", "bihrt_framebuffer_resolve", "bihrt_render_hits", "bihrt_secondary_rays", "bihrt_framebuffer", "bihrt_framebuffer_read",
+    "bihrt_render", "bihrt_render_counted", "bihrt_render_shard", "bihrt_render_samples", "bihrt_render_interleaved", "bihrt_render_interleaved_to", "bihrt_framebuffer_ipc_export", "bihrt_framebuffer_ipc_open", "bihrt_framebuffer_ipc_close", "bihrt_bih_region", "bihrt_bih_adopt", "bihrt_framebuffer_resolve", "bihrt_render_hits", "bihrt_secondary_rays", "bihrt_framebuffer", "bihrt_framebuffer_read",
     "bihrt_bih_blob_bytes", "bihrt_bih_export", "bihrt_bih_import",
 ]
 
@@ -344,6 +344,15 @@ class Renderer:
 
     def bih_export(self, dev_buffer, nbytes):
         self._check(self._lib.bihrt_bih_export(self._ctx, _ptr(dev_buffer), C.c_uint64(nbytes)))
+
+    def bih_region(self, n):
+        """(device pointer, bytes) of the whole blob of an n-triangle scene, laid out (and allocated) for n."""
+        p, b = C.c_void_p(), C.c_uint64()
+        self._check(self._lib.bihrt_bih_region(self._ctx, C.c_int64(n), C.byref(p), C.byref(b)))
+        return p.value, b.value
+
+    def bih_adopt(self, n):
+        self._check(self._lib.bihrt_bih_adopt(self._ctx, C.c_int64(n)))
 
     def bih_import(self, dev_buffer, nbytes):
         self._check(self._lib.bihrt_bih_import(self._ctx, _ptr(dev_buffer), C.c_uint64(nbytes)))

@@ -98,6 +98,22 @@ def frame_barrier(dist, token):
     dist.all_reduce(token)
 
 
+def replicate_bih_inplace(renderer, dist, n, src=0):
+    """Broadcast the BIH of an n-triangle scene built on rank `src` straight between the contexts' blobs: one
+    collective, no staging copies, no host synchronisation (n must be known on every rank).  Returns the bytes."""
+    import torch
+    if hasattr(renderer, "bih_region_tensor"):          # test doubles hand out their own (CPU) tensor
+        blob = renderer.bih_region_tensor(n)
+        nbytes = blob.numel()
+    else:
+        ptr, nbytes = renderer.bih_region(n)
+        blob = torch.as_tensor(_CudaView(ptr, (nbytes,), "|u1"), device="cuda:%d" % renderer.device)
+    dist.broadcast(blob, src=src)
+    if dist.get_rank() != src:
+        renderer.bih_adopt(n)
+    return nbytes
+
+
 def gather_framebuffer(fb, dist, dst=0):
     """Combine the ranks' disjoint shards (0 outside a rank's tiles) on rank `dst`: one reduce."""
     dist.reduce(fb, dst=dst, op=dist.ReduceOp.SUM)

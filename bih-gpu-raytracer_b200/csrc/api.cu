@@ -208,6 +208,10 @@ int bihrt_scene_load_triangles(bihrt_ctx* c, const float* xyz9, int64_t n) {
     if (n >= BIH_MAX_TRIS) return bihrt_fail(c, BIHRT_ERR_INVALID, "at most 2^29-1 triangles (29-bit child references)");
     int rc = ensure_capacity(c, n, true);
     if (rc) return rc;
+    if (n != c->n) {                       // the blob is laid out for n: [header | n node slots | n triangle records]
+        bind_blob(c, std::max<int64_t>(n, 1));
+        if (c->build_graph_exec) { cudaGraphExecDestroy(c->build_graph_exec); c->build_graph_exec = nullptr; }
+    }
     c->n = n; c->have_scene = true; c->built = false; c->topology_valid = false;
     return upload_triangles(c, xyz9, n);
 }
@@ -726,11 +730,43 @@ int bihrt_bih_import(bihrt_ctx* c, const void* dev_src, uint64_t bytes) {
     if (h.nu > h.n || bytes < 64 + nb + tb) return bihrt_fail(c, BIHRT_ERR_INVALID, "blob truncated or corrupt");
     int rc = ensure_capacity(c, h.n, false);
     if (rc) return rc;
+    if ((int64_t)h.n != c->n) {
+        bind_blob(c, std::max<int64_t>(h.n, 1));
+        if (c->build_graph_exec) { cudaGraphExecDestroy(c->build_graph_exec); c->build_graph_exec = nullptr; }
+        c->have_scene = false;
+    }
     const uint8_t* s = (const uint8_t*)dev_src;
     BIHRT_CUDA(c, cudaMemcpyAsync(c->d_hdr, s, 64, cudaMemcpyDeviceToDevice, c->stream));
     if (nb) BIHRT_CUDA(c, cudaMemcpyAsync(c->d_nodes, s + 64, nb, cudaMemcpyDeviceToDevice, c->stream));
     if (tb) BIHRT_CUDA(c, cudaMemcpyAsync(c->d_tris, s + 64 + nb, tb, cudaMemcpyDeviceToDevice, c->stream));
     c->n = h.n; c->built = true; c->build_timed = false; c->topology_valid = false;
+    return BIHRT_OK;
+}
+
+// In-place replication: the whole blob of an n-triangle scene, [header 64 B | n node slots | n triangle records], is one
+// contiguous region whose size follows from n alone, so it can be the buffer of a broadcast on every rank: no export /
+// import copies and no host read of Nu.  bihrt_bih_region lays the context's blob out for n triangles (allocating if
+// needed) and returns the region; on the building rank (same n, already built) it changes nothing.  After the
+// broadcast the receivers call bihrt_bih_adopt.
+int bihrt_bih_region(bihrt_ctx* c, int64_t n, void** dev_ptr, uint64_t* bytes) {
+    ENTER(c);
+    if (n < 0 || n >= BIH_MAX_TRIS || !dev_ptr || !bytes) return BIHRT_ERR_INVALID;
+    int rc = ensure_capacity(c, n, false);
+    if (rc) return rc;
+    if (n != c->n) {
+        bind_blob(c, std::max<int64_t>(n, 1));
+        if (c->build_graph_exec) { cudaGraphExecDestroy(c->build_graph_exec); c->build_graph_exec = nullptr; }
+        c->n = n; c->have_scene = false; c->built = false; c->topology_valid = false;
+    }
+    *dev_ptr = c->d_blob;
+    *bytes = 64 + (uint64_t)std::max<int64_t>(n, 1) * 16 + (uint64_t)n * 48;
+    return BIHRT_OK;
+}
+
+int bihrt_bih_adopt(bihrt_ctx* c, int64_t n) {
+    ENTER(c);
+    if (n != c->n || !c->d_blob) return bihrt_fail(c, BIHRT_ERR_STATE, "bihrt_bih_adopt(%lld) without a matching bihrt_bih_region", (long long)n);
+    c->built = true; c->build_timed = false; c->topology_valid = false;
     return BIHRT_OK;
 }
 

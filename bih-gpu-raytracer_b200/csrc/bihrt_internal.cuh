@@ -110,7 +110,7 @@ struct bihrt_ctx {
     int opt_vote_wait = 1, opt_vote_walk = 3;
     int opt_lane_groups = -1; // samples of a pixel across lanes: -1 auto (as many as divide the sample count, <= 32), else 2^k
     int opt_interleave_chunk = 8;  // multi-GPU unit interleave: consecutive units per run (power of two; reduced until it divides a tile)
-    int opt_tile_order = 1; // camera modes: start the tiles that were expensive in the previous frame first (1: launches of 1 M .. 48 M rays, 2: always, 0: never)
+    int opt_tile_order = 1; // camera modes: start the tiles that were expensive in the previous frame first (1: launches of 64 k .. 48 M rays on scenes of >= 10 k triangles, 2: always, 0: never)
     int opt_sm_queues = -1; // 1: per-SM work queues (tile locality in L1), 0: one global counter, -1: by launch size
     int64_t kernel_launches = 0;
     int opt_build_graph = 1;            // replay the build as a captured CUDA graph

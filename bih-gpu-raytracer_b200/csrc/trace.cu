@@ -530,9 +530,9 @@ int bihrt_trace_launch(bihrt_ctx* c, const TraceArgs& a_in, int mode, bool count
     // cost-ordered tiles (camera modes, one global counter): reuse the order measured by the previous launch of the same
     // frame geometry; always record the costs of this one
     uint32_t ntiles = 0;
-    // (launches of tens of milliseconds have no tail to speak of and lose ~0.5 % to the changed tile neighbourhood; for
-    // launches of a few hundred thousand rays the extra k_tile_order launch costs more than the order gains)
-    if (mode != 0 && a.queues == 1 && (c->opt_tile_order > 1 || (c->opt_tile_order == 1 && rays >= (1ll << 20) && rays < (48ll << 20)))) {
+    // (launches of tens of milliseconds have no tail to speak of and lose ~0.5 % to the changed tile neighbourhood; tiny
+    // scenes have no long units -- the Cornell box frame is 25 us -- and only pay for the extra k_tile_order launch)
+    if (mode != 0 && a.queues == 1 && (c->opt_tile_order > 1 || (c->opt_tile_order == 1 && rays >= (64ll << 10) && rays < (48ll << 20) && c->n >= 10000))) {
         const int tx = (a.w + 31) / 32, ty = (a.h + 31) / 32, T = tx * ty;
         const int mine = T > a.shard_index ? (T - a.shard_index + a.shard_count - 1) / a.shard_count : 0;
         if (mine > 1 && mine <= 65536) {

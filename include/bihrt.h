@@ -209,6 +209,13 @@ BIHRT_API int bihrt_bih_blob_bytes(bihrt_ctx* ctx, uint64_t* bytes);            
 BIHRT_API int bihrt_bih_export(bihrt_ctx* ctx, void* dev_dst, uint64_t bytes);           /* device buffer, D2D on the ctx stream */
 BIHRT_API int bihrt_bih_import(bihrt_ctx* ctx, const void* dev_src, uint64_t bytes);     /* adopt a blob built on another GPU */
 
+/* In place: the blob of an n-triangle scene is one contiguous device region whose size follows from n alone, so it can be
+ * the buffer of the broadcast on every rank (no export / import copies, no host read of Nu).  bihrt_bih_region lays the
+ * context's blob out for n triangles and returns the region (a no-op on the rank that built an n-triangle scene);
+ * receivers call bihrt_bih_adopt(n) once the broadcast has been enqueued on the context's stream. */
+BIHRT_API int bihrt_bih_region(bihrt_ctx* ctx, int64_t n, void** dev_ptr, uint64_t* bytes);
+BIHRT_API int bihrt_bih_adopt(bihrt_ctx* ctx, int64_t n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -50,6 +50,16 @@ class FakeRenderer:
     def sync(self):
         pass
 
+    # in-place replication: the blob region of an n-triangle scene is the broadcast buffer itself
+    def bih_region_tensor(self, n):
+        import torch
+        if getattr(self, "region", None) is None:
+            self.region = torch.from_numpy((np.arange(64 + 64 * n) % 251).astype(np.uint8)) if self.rank == 0 else torch.zeros(64 + 64 * n, dtype=torch.uint8)
+        return self.region
+
+    def bih_adopt(self, n):
+        self.adopted = n
+
 
 def _worker(rank, world, port, q):
     import torch
@@ -62,6 +72,12 @@ def _worker(rank, world, port, q):
         r = FakeRenderer(rank)
         n = multi.replicate_bih(r, dist, src=0, device="cpu")
         ok_blob = n == 1000 and (rank == 0 or np.array_equal(r.imported, np.arange(1000, dtype=np.uint8)))
+        nb = multi.replicate_bih_inplace(r, dist, 37, src=0)
+        ok_blob = ok_blob and nb == 64 + 64 * 37 and np.array_equal(r.region.numpy(), (np.arange(nb) % 251).astype(np.uint8)) \
+            and (rank == 0 or getattr(r, "adopted", None) == 37) and (rank != 0 or not hasattr(r, "adopted"))
+        tok = torch.ones(1, dtype=torch.int32)
+        multi.frame_barrier(dist, tok)
+        ok_blob = ok_blob and int(tok.item()) == world
         # framebuffer gather: each rank holds its own tiles of a known image, 0 elsewhere
         w, h = 200, 120
         full = (np.arange(w * h, dtype=np.int32).reshape(h, w) % 9973) + 1

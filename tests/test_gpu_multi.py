@@ -46,6 +46,17 @@ def test_two_gpus_render_the_same_image(scenes):
             multi.framebuffer_tensor(r0).copy_(torch.from_numpy(total.astype(np.int32)).to("cuda:0"))
             torch.cuda.synchronize(0)
             np.testing.assert_array_equal(r0.framebuffer_resolve(spp).framebuffer(), full)
+    # in-place replication: the blob region of device 0 copied straight into device 1's region, then adopted
+    r2 = bihrt.Renderer(1)
+    p0, nb0 = r0.bih_region(len(tri))
+    p2, nb2 = r2.bih_region(len(tri))
+    assert nb0 == nb2 == 64 + 64 * len(tri)
+    src = torch.as_tensor(multi._CudaView(p0, (nb0,), "|u1"), device="cuda:0")
+    dst = torch.as_tensor(multi._CudaView(p2, (nb2,), "|u1"), device="cuda:1")
+    r0.sync(); dst.copy_(src); torch.cuda.synchronize(0); torch.cuda.synchronize(1)
+    r2.bih_adopt(len(tri))
+    np.testing.assert_array_equal(r2.render(cam, w, h, spp=spp, jitter=True).framebuffer(), full)
+    r2.close()
     # fused gather: device 1's trace kernel stores its pixels straight into device 0's framebuffer (peer access)
     r0.render(cam, w, h, spp=1); r0.sync()
     ptr0 = r0.framebuffer_ptr()[0]
