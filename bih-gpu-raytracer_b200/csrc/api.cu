@@ -46,9 +46,9 @@ static int fetch(bihrt_ctx* c, std::vector<T>& dst, const T* src, size_t count) 
 }
 
 static size_t lookback_words_for(int64_t n) {
-    // must match build.cu: 4 onesweep passes x tiles(4096) x 256 + rle tiles(2048)
+    // must match build.cu: 4 onesweep passes x tiles(4096) x 256 + 8 words per rle tile(2048)
     size_t os_tiles = (size_t)((n + 4095) / 4096), rle_tiles = (size_t)((n + 2047) / 2048);
-    return 4 * os_tiles * 256 + rle_tiles + 16;
+    return 4 * os_tiles * 256 + rle_tiles * 8 + 16;
 }
 
 static size_t blob_capacity(int64_t n) { return 64 + (size_t)n * 16 + (size_t)n * 48 + 64; }

@@ -8,8 +8,9 @@
 //   k_scene_box   scene AABB                                   36 B read per triangle
 //   k_morton      AABB centre -> 30-bit Morton key, fused 4x256 digit histogram   36 R + 4 W
 //   k_onesweep x4 stable LSD radix sort, 8-bit digits, decoupled look-back       16 R + 16 W per pass
-//   k_rle_*       head flags -> unique codes, first slot of each leaf, Nu (count, scan, write)  8 R + <=8 W
-//   k_reorder     per slot: gather the triangle, write its 48-byte leaf-ordered record and its AABB as the
+//   k_rle_*       head flags per 256-slot block, scanned -> Nu and the leaf number at every block start      4 R
+//   k_reorder     per slot: leaf heads -> unique codes + first slot of each leaf (the RLE write, fused);
+//                 gather the triangle, write its 48-byte leaf-ordered record and its AABB as the
 //                 bottom level of six implicit min/max heaps (+8 levels per block)   4+36 R + 48+~48 W
 //   k_heap_up     upper heap levels (8 per launch)
 //   k_nodes       per node: Karras range/split search + two heap range queries for the clip planes,
@@ -90,7 +91,10 @@ __device__ __forceinline__ void minmax3(float a, float b, float c, float& mn, fl
 #define H_WORDS     1040
 
 // ------------------------------------------------------------------------------------------
-__global__ void k_init(uint32_t* hist, uint32_t* enc, BihHeader* hdr, uint32_t n) {
+// also clears the look-back words of the four sort passes (one launch instead of a kernel + a memset node)
+__global__ void __launch_bounds__(256) k_init(uint32_t* hist, uint32_t* enc, BihHeader* hdr, uint32_t n, uint4* __restrict__ lookback, uint32_t lb_vec4) {
+    for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < lb_vec4; i += gridDim.x * 256u) lookback[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (blockIdx.x != 0) return;
     for (int i = threadIdx.x; i < H_WORDS; i += blockDim.x) hist[i] = 0;
     if (threadIdx.x < 3) { enc[threadIdx.x] = 0xFFFFFFFFu; enc[3 + threadIdx.x] = 0u; }
     if (threadIdx.x == 0) { hdr->n = n; hdr->nu = 0; hdr->status = 0; hdr->root_axis = 0; }
@@ -375,14 +379,12 @@ __device__ __forceinline__ uint32_t rle_heads(const uint32_t* __restrict__ keys,
 }
 
 __global__ void __launch_bounds__(256) k_rle_count(const uint32_t* __restrict__ keys, uint32_t n, uint32_t* __restrict__ tile_cnt) {
-    __shared__ uint32_t s_w[8];
     uint32_t key[RLE_ITEMS], cnt;
     rle_heads(keys, n, blockIdx.x * RLE_TILE + threadIdx.x * RLE_ITEMS, key, cnt);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(FULL, cnt, o);
-    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = cnt;
-    __syncthreads();
-    if (threadIdx.x == 0) { uint32_t t = 0; for (int i = 0; i < 8; i++) t += s_w[i]; tile_cnt[blockIdx.x] = t; }
+    // a warp's 32 threads x 8 keys are 256 consecutive slots = one block of k_reorder, which writes the leaves
+    if ((threadIdx.x & 31) == 0) tile_cnt[blockIdx.x * 8u + (threadIdx.x >> 5)] = cnt;
 }
 
 // exclusive scan of the tile counts in place (one block), Nu and the sentinel first[Nu] = n
@@ -410,19 +412,6 @@ __global__ void __launch_bounds__(1024) k_rle_scan(uint32_t* __restrict__ tile_c
     if (threadIdx.x == 0) { const uint32_t nu = s_carry; hdr->nu = nu; first[nu] = n; }
 }
 
-__global__ void __launch_bounds__(256) k_rle_write(const uint32_t* __restrict__ keys, uint32_t n, const uint32_t* __restrict__ tile_off,
-                                                   uint32_t* __restrict__ umc, uint32_t* __restrict__ first) {
-    __shared__ uint32_t s_w[8];
-    const uint32_t g0 = blockIdx.x * RLE_TILE + threadIdx.x * RLE_ITEMS;
-    uint32_t key[RLE_ITEMS], cnt, total;
-    const uint32_t heads = rle_heads(keys, n, g0, key, cnt);
-    uint32_t k = tile_off[blockIdx.x] + block_excl_scan_256(cnt, s_w, &total);
-#pragma unroll
-    for (int i = 0; i < RLE_ITEMS; i++) {
-        if (heads & (1u << i)) { umc[k] = key[i]; first[k] = g0 + i; k++; }
-    }
-}
-
 // ------------------------------------------------------------------------------------------
 // Leaves, tree and clip planes without any inter-thread dependency:
 //   k_reorder     thread per sorted slot: the triangle's AABB becomes the bottom level of six implicit binary
@@ -446,49 +435,75 @@ struct Box { float lo[3], hi[3]; };
 // root, the per-slot triangle boxes sit at [P, 2P).  Entries whose subtree holds no slot below n are never
 // read by a range query inside [0, n) and are left unwritten.
 
-// One block reduces 256 consecutive elements of the level that starts at heap index `in_base` through
-// up to 8 further levels (s[][] holds the 256 inputs on entry).
-__device__ __forceinline__ void heap_reduce_block(float (*s)[256], float* __restrict__ heaps, uint32_t P, uint32_t in_base) {
-    uint32_t width = 128, level_base = in_base >> 1;
-    for (; level_base >= 1; width >>= 1, level_base >>= 1) {
-        __syncthreads();
-        float r[6];
-        const bool act = threadIdx.x < width && (blockIdx.x * width + threadIdx.x) < level_base;
-        if (act) {
+// One block reduces 256 consecutive elements of the level that starts at heap index `in_base` through up to 8 further
+// levels: r[] holds this thread's element on entry (3 maxima, 3 minima).  Five levels inside each warp with shuffles,
+// three more over the 8 warp results: two block barriers instead of sixteen.
+__device__ __forceinline__ void heap_reduce_block(float r[6], float (*s)[8], float* __restrict__ heaps, uint32_t P, uint32_t in_base) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t level_base = in_base;
+#pragma unroll
+    for (int l = 1; l <= 5; l++) {
+        level_base >>= 1;
+        if (level_base == 0) return;                              // above the root (warp-uniform)
+#pragma unroll
+        for (int c = 0; c < 6; c++) {
+            const float y = __shfl_xor_sync(FULL, r[c], 1 << (l - 1));
+            r[c] = c < 3 ? fmaxf(r[c], y) : fminf(r[c], y);
+        }
+        const uint32_t i = (blockIdx.x * 256u + threadIdx.x) >> l;    // element of this level
+        if ((lane & ((1 << l) - 1)) == 0 && i < level_base) {
+#pragma unroll
+            for (int c = 0; c < 6; c++) heaps[(size_t)c * 2 * P + level_base + i] = r[c];
+        }
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int c = 0; c < 6; c++) s[c][w] = r[c];
+    }
+    __syncthreads();
+    if (w == 0) {
+#pragma unroll
+        for (int c = 0; c < 6; c++) r[c] = lane < 8 ? s[c][lane] : (c < 3 ? -INFINITY : INFINITY);
+#pragma unroll
+        for (int l = 6; l <= 8; l++) {
+            level_base >>= 1;
+            if (level_base == 0) return;
 #pragma unroll
             for (int c = 0; c < 6; c++) {
-                const float x = s[c][2 * threadIdx.x], y = s[c][2 * threadIdx.x + 1];
-                r[c] = c < 3 ? fmaxf(x, y) : fminf(x, y);
+                const float y = __shfl_xor_sync(FULL, r[c], 1 << (l - 6));
+                r[c] = c < 3 ? fmaxf(r[c], y) : fminf(r[c], y);
             }
-        }
-        __syncthreads();
-        if (act) {
+            const uint32_t i = (blockIdx.x * 8u + lane) >> (l - 5);
+            if (lane < 8 && (lane & ((1 << (l - 5)) - 1)) == 0 && i < level_base) {
 #pragma unroll
-            for (int c = 0; c < 6; c++) {
-                s[c][threadIdx.x] = r[c];
-                heaps[(size_t)c * 2 * P + level_base + blockIdx.x * width + threadIdx.x] = r[c];
+                for (int c = 0; c < 6; c++) heaps[(size_t)c * 2 * P + level_base + i] = r[c];
             }
         }
-        if (width == 1) break;
     }
 }
 
 // Leaf-ordered triangle records + bottom heap levels: one thread per sorted slot gathers its input triangle
 // (36 B), writes the 48-byte record (coalesced) and the triangle's AABB (std::minmax semantics of
 // R/src/App.cpp:123-127) as heap level 0.  end-of-leaf = the next slot has a different Morton code.
+template <bool RLE>
 __global__ void __launch_bounds__(256) k_reorder(const float* __restrict__ tri_in, const uint32_t* __restrict__ idx_sorted,
                                                  const uint32_t* __restrict__ keys_sorted, uint32_t n, BihTri* __restrict__ tris,
-                                                 float* __restrict__ heaps, uint32_t P) {
-    __shared__ float s[6][256];
+                                                 float* __restrict__ heaps, uint32_t P, const uint32_t* __restrict__ tile_off,
+                                                 uint32_t* __restrict__ umc, uint32_t* __restrict__ first) {
+    __shared__ float s[6][8];
+    __shared__ uint32_t s_w[8];
     const uint32_t j = blockIdx.x * 256u + threadIdx.x;
     float mn[3] = { INFINITY, INFINITY, INFINITY }, mx[3] = { -INFINITY, -INFINITY, -INFINITY };
+    uint32_t key = 0, head = 0;
     if (j < n) {
         const uint32_t p = idx_sorted[j];
         const float* t = tri_in + (size_t)p * 9;
         float v[9];
 #pragma unroll
         for (int i = 0; i < 9; i++) v[i] = __ldg(t + i);
-        const uint32_t last = (j + 1 == n || keys_sorted[j + 1] != keys_sorted[j]) ? 1u : 0u;
+        key = keys_sorted[j];
+        const uint32_t last = (j + 1 == n || keys_sorted[j + 1] != key) ? 1u : 0u;
+        if (RLE) head = (j == 0 || keys_sorted[j - 1] != key) ? 1u : 0u;
         float4* dst = reinterpret_cast<float4*>(tris + j);
         __stcs(dst, make_float4(v[0], v[1], v[2], __fsub_rn(v[3], v[0])));
         __stcs(dst + 1, make_float4(__fsub_rn(v[4], v[1]), __fsub_rn(v[5], v[2]), __fsub_rn(v[6], v[0]), __fsub_rn(v[7], v[1])));
@@ -502,19 +517,26 @@ __global__ void __launch_bounds__(256) k_reorder(const float* __restrict__ tri_i
             heaps[(size_t)(3 + a) * 2 * P + P + j] = mn[a];
         }
     }
-#pragma unroll
-    for (int a = 0; a < 3; a++) { s[a][threadIdx.x] = mx[a]; s[3 + a][threadIdx.x] = mn[a]; }
-    heap_reduce_block(s, heaps, P, P);
+    if (RLE) {
+        // run-length encoding of the sorted keys (thrust::reduce_by_key + unique_by_key_copy, R/src/Renderer.cpp:450-472):
+        // this slot starts leaf k = heads before it; k_rle_count / k_rle_scan supplied the heads before this block
+        uint32_t total;
+        const uint32_t k = tile_off[blockIdx.x] + block_excl_scan_256(head, s_w, &total);
+        if (head) { umc[k] = key; first[k] = j; }
+    }
+    float r[6] = { mx[0], mx[1], mx[2], mn[0], mn[1], mn[2] };
+    heap_reduce_block(r, s, heaps, P, P);
 }
 
 // 8 more levels above the level of `in_count` used elements that starts at heap index `in_base`
 __global__ void __launch_bounds__(256) k_heap_up(float* __restrict__ heaps, uint32_t P, uint32_t in_base, uint32_t in_count) {
-    __shared__ float s[6][256];
+    __shared__ float s[6][8];
     const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+    float r[6];
 #pragma unroll
     for (int c = 0; c < 6; c++)
-        s[c][threadIdx.x] = i < in_count ? heaps[(size_t)c * 2 * P + in_base + i] : (c < 3 ? -INFINITY : INFINITY);
-    heap_reduce_block(s, heaps, P, in_base);
+        r[c] = i < in_count ? heaps[(size_t)c * 2 * P + in_base + i] : (c < 3 ? -INFINITY : INFINITY);
+    heap_reduce_block(r, s, heaps, P, in_base);
 }
 
 template <bool IS_MAX>
@@ -587,14 +609,16 @@ int bihrt_build_launch(bihrt_ctx* c) {
     cudaStream_t st = c->stream;
     const uint32_t os_tiles = (n + OS_TILE - 1) / OS_TILE;
     const uint32_t rle_tiles = (n + RLE_TILE - 1) / RLE_TILE;
-    const size_t lb_words = (size_t)4 * os_tiles * 256 + rle_tiles;
+    const uint32_t rle_blocks = rle_tiles * 8;                     // 256-slot blocks (k_reorder's), rounded up to whole RLE tiles
+    const size_t lb_words = (size_t)4 * os_tiles * 256 + rle_blocks;
     if (lb_words > c->lookback_words) return bihrt_fail(c, BIHRT_ERR_INTERNAL, "look-back buffer too small");
 
     int pe = 0;
 #define PROF_MARK() do { if (c->opt_profile && pe < BIHRT_PROF_EVENTS) cudaEventRecord(c->prof_ev[pe++], st); } while (0)
     PROF_MARK();
-    k_init<<<1, 256, 0, st>>>(c->d_hist, c->d_scenebox_enc, c->d_hdr, n);
-    BIHRT_CUDA(c, cudaMemsetAsync(c->d_lookback, 0, lb_words * 4, st));
+    const uint32_t lb_vec4 = (uint32_t)((lb_words + 3) / 4);        // the buffer is allocated with 16 spare words
+    k_init<<<(int)max(1u, min((uint32_t)c->sm_count, (lb_vec4 + 1023u) / 1024u)), 256, 0, st>>>(c->d_hist, c->d_scenebox_enc, c->d_hdr, n,
+                                                                                      reinterpret_cast<uint4*>(c->d_lookback), lb_vec4);
     PROF_MARK();   // 1: after init + memsets
     const int stream_grid = (int)max(1u, min((uint32_t)(c->sm_count * 3), ((n >> 2) + 255) / 256));
     k_scene_box<<<stream_grid, 256, 0, st>>>(c->d_tri_in, n, c->d_scenebox_enc);
@@ -614,14 +638,13 @@ int bihrt_build_launch(bihrt_ctx* c) {
     // 4 passes: sorted data is back in buffer 0
     uint32_t* tile_cnt = c->d_lookback + (size_t)4 * os_tiles * 256;
     k_rle_count<<<rle_tiles, 256, 0, st>>>(c->d_keys[cur], n, tile_cnt);
-    k_rle_scan<<<1, 1024, 0, st>>>(tile_cnt, rle_tiles, n, c->d_first, c->d_hdr);
-    k_rle_write<<<rle_tiles, 256, 0, st>>>(c->d_keys[cur], n, tile_cnt, c->d_umc, c->d_first);
+    k_rle_scan<<<1, 1024, 0, st>>>(tile_cnt, rle_blocks, n, c->d_first, c->d_hdr);
     PROF_MARK();   // 8: after rle
     // heaps are padded to a power of two >= n (Nu <= n is only known on the device)
     uint32_t P = 256;
     while (P < n) P <<= 1;
-    k_reorder<<<(n + 255) / 256, 256, 0, st>>>(c->d_tri_in, c->d_vals[cur], c->d_keys[cur], n, c->d_tris, c->d_heaps, P);
-    PROF_MARK();   // 9: after reorder + slot boxes
+    k_reorder<true><<<(n + 255) / 256, 256, 0, st>>>(c->d_tri_in, c->d_vals[cur], c->d_keys[cur], n, c->d_tris, c->d_heaps, P, tile_cnt, c->d_umc, c->d_first);
+    PROF_MARK();   // 9: after reorder + slot boxes + leaves
     int launches = 0;
     for (uint32_t lvl = P >> 8, used = (n + 255) / 256; lvl > 1; lvl >>= 8, used = (used + 255) / 256) {   // level with `lvl` elements
         k_heap_up<<<(used + 255) / 256, 256, 0, st>>>(c->d_heaps, P, lvl, used);
@@ -632,7 +655,7 @@ int bihrt_build_launch(bihrt_ctx* c) {
     PROF_MARK();   // 11: after nodes
     PROF_MARK();   // 12: after reorder
     c->prof_count = pe;
-    c->kernel_launches += 12 + launches;   // k_init, k_scene_box, k_morton, 4 x k_onesweep, 3 x k_rle_*, k_reorder, k_heap_up.., k_nodes
+    c->kernel_launches += 11 + launches;   // k_init, k_scene_box, k_morton, 4 x k_onesweep, k_rle_count, k_rle_scan, k_reorder, k_heap_up.., k_nodes
     BIHRT_CUDA(c, cudaGetLastError());
     return BIHRT_OK;
 }
@@ -660,7 +683,7 @@ int bihrt_refit_launch(bihrt_ctx* c) {
     k_refit_init<<<1, 32, 0, st>>>(c->d_scenebox_enc);
     k_scene_box<<<stream_grid, 256, 0, st>>>(c->d_tri_in, n, c->d_scenebox_enc);
     k_refit_box<<<1, 32, 0, st>>>(c->d_scenebox_enc, c->d_hdr);
-    k_reorder<<<(n + 255) / 256, 256, 0, st>>>(c->d_tri_in, c->d_vals[0], c->d_keys[0], n, c->d_tris, c->d_heaps, P);
+    k_reorder<false><<<(n + 255) / 256, 256, 0, st>>>(c->d_tri_in, c->d_vals[0], c->d_keys[0], n, c->d_tris, c->d_heaps, P, nullptr, nullptr, nullptr);
     int launches = 0;
     for (uint32_t lvl = P >> 8, used = (n + 255) / 256; lvl > 1; lvl >>= 8, used = (used + 255) / 256) {
         k_heap_up<<<(used + 255) / 256, 256, 0, st>>>(c->d_heaps, P, lvl, used);
