@@ -494,6 +494,9 @@ def run_ours(args, rank, world, local_rank):
                 os_ = torch.empty(len(db), dtype=torch.int32, device=dev)
                 ms_b = med(lambda: r.trace(db, t=ot, slot=os_, prim=os_))
                 e[nm + "_mrays_s"] = len(db) / (ms_b * 1e-3) / 1e6
+                if nm == "shadow":      # occlusion query: is the light (t = 1) hidden -- ends at the first blocker
+                    ms_o = med(lambda: r.trace_any(db, tmax=1.0, blocker=os_))
+                    e["shadow_occlusion_mrays_s"] = len(db) / (ms_o * 1e-3) / 1e6
                 e[nm + "_rays"] = len(db)
                 e[nm + "_generation_ms"] = med(lambda: r.secondary_rays(ca, 1920, 1080, spp=1, kind=kind, light=(0.0, 0.8, 0.0)), 3)
             configs["config3_atrium_262k_1080p"] = e

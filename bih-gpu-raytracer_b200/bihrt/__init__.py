@@ -64,7 +64,7 @@ class BuildInfo(C.Structure):
 ABI_SYMBOLS = [
     "bihrt_version", "bihrt_create", "bihrt_destroy", "bihrt_last_error", "bihrt_set_stream", "bihrt_sync",
     "bihrt_set_option", "bihrt_get_stat", "bihrt_scene_load_triangles", "bihrt_scene_update_vertices", "bihrt_scene_load_obj",
-    "bihrt_build", "bihrt_refit", "bihrt_get_build_info", "bihrt_export_reference_view", "bihrt_trace", "bihrt_trace_counted",
+    "bihrt_build", "bihrt_refit", "bihrt_get_build_info", "bihrt_export_reference_view", "bihrt_trace", "bihrt_trace_any", "bihrt_trace_counted",
     "bihrt_render", "bihrt_render_counted", "bihrt_render_shard", "bihrt_render_samples", "bihrt_render_interleaved", "bihrt_render_interleaved_to", "bihrt_framebuffer_ipc_export", "bihrt_framebuffer_ipc_open", "bihrt_framebuffer_ipc_close", "bihrt_bih_region", "bihrt_bih_adopt", "bihrt_framebuffer_resolve", "bihrt_render_hits", "bihrt_secondary_rays", "bihrt_framebuffer", "bihrt_framebuffer_read",
     "bihrt_bih_blob_bytes", "bihrt_bih_export", "bihrt_bih_import",
 ]
@@ -238,6 +238,19 @@ class Renderer:
             return t, slot, prim, {"nodes": cnt[0], "tris": cnt[1], "max_stack": cnt[2], "rays": cnt[3]}
         self._check(self._lib.bihrt_trace(self._ctx, _ptr(rays), C.c_int64(n), _ptr(t), _ptr(slot), _ptr(prim)))
         return t, slot, prim
+
+    def trace_any(self, rays, tmax=1.0, blocker=None):
+        """Occlusion query: blocker[i] >= 0 iff ray i hits something with 0 < t < tmax (bihrt_trace_any)."""
+        if isinstance(rays, np.ndarray):
+            rays = np.ascontiguousarray(rays, dtype=np.float32)
+            n = rays.size // 6
+            blocker = np.empty(n, np.int32) if blocker is None else blocker
+        else:
+            import torch
+            n = rays.numel() // 6
+            blocker = torch.empty(n, dtype=torch.int32, device=rays.device) if blocker is None else blocker
+        self._check(self._lib.bihrt_trace_any(self._ctx, _ptr(rays), C.c_int64(n), C.c_float(tmax), _ptr(blocker)))
+        return blocker
 
     def render(self, camera, w, h, spp=1, seed=1984, jitter=False, shard=(0, 1)):
         cam = camera if isinstance(camera, Camera) else Camera.from_array(camera)

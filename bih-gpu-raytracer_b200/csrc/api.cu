@@ -436,7 +436,8 @@ static int unstage_outputs(bihrt_ctx* c, int64_t n, const OutStage& o) {
     return BIHRT_OK;
 }
 
-static int trace_impl(bihrt_ctx* c, const bihrt_ray* rays, int64_t n, float* t, int32_t* slot, int32_t* prim, uint64_t* counters) {
+static int trace_impl(bihrt_ctx* c, const bihrt_ray* rays, int64_t n, float* t, int32_t* slot, int32_t* prim, uint64_t* counters,
+                      bool any_hit = false, float tmax = 0.f) {
     ENTER(c);
     if (!c->built) return bihrt_fail(c, BIHRT_ERR_STATE, "BIH not built");
     if (n < 0 || (n > 0 && !rays)) return bihrt_fail(c, BIHRT_ERR_INVALID, "bad ray array");
@@ -451,6 +452,7 @@ static int trace_impl(bihrt_ctx* c, const bihrt_ray* rays, int64_t n, float* t, 
         if (rays_dev) a.rays = rays;
         else { BIHRT_CUDA(c, cudaMemcpyAsync(front, rays, (size_t)n * sizeof(bihrt_ray), cudaMemcpyHostToDevice, c->stream)); a.rays = (const bihrt_ray*)front; }
         a.nrays = n; a.out_t = o.t; a.out_slot = o.slot; a.out_prim = o.prim;
+        a.any_hit = any_hit ? 1 : 0; a.tmax = tmax;
         if ((rc = bihrt_trace_launch(c, a, 0, counters != nullptr))) return rc;
         if ((rc = unstage_outputs(c, n, o))) return rc;
     }
@@ -469,6 +471,15 @@ int bihrt_trace(bihrt_ctx* c, const bihrt_ray* rays, int64_t n, float* t, int32_
 int bihrt_trace_counted(bihrt_ctx* c, const bihrt_ray* rays, int64_t n, float* t, int32_t* slot, int32_t* prim, uint64_t counters[4]) {
     if (!counters) return BIHRT_ERR_INVALID;
     return trace_impl(c, rays, n, t, slot, prim, counters);
+}
+
+// Occlusion query for shadow rays: blocker[i] = slot of SOME triangle the ray hits with 0 < t < tmax, or -1.  The
+// traversal is pruned at tmax and stops at the first such hit, so blocker[i] >= 0 exactly when the closest hit of
+// bihrt_trace has t < tmax; which blocker is reported is unspecified.
+int bihrt_trace_any(bihrt_ctx* c, const bihrt_ray* rays, int64_t n, float tmax, int32_t* blocker) {
+    if (!c) return BIHRT_ERR_INVALID;
+    if (!(tmax > 0.f)) return bihrt_fail(c, BIHRT_ERR_INVALID, "tmax must be positive");
+    return trace_impl(c, rays, n, nullptr, blocker, nullptr, nullptr, true, tmax);
 }
 
 static int render_check(bihrt_ctx* c, const bihrt_camera* cam, int w, int h, int spp, int si, int sc) {

@@ -131,6 +131,7 @@ int bihrt_refit_launch(bihrt_ctx* c);
 struct TraceArgs {
     const BihHeader* hdr; const BihNode* nodes; const BihTri* tris;
     const bihrt_ray* rays; int64_t nrays;
+    int any_hit; float tmax;  // ray lists: occlusion query -- some hit with 0 < t < tmax, not the closest one
     float* out_t; int32_t* out_slot; int32_t* out_prim;
     // camera mode
     bihrt_camera cam; int w, h, spp; uint64_t seed; uint32_t flags; int shard_index, shard_count;

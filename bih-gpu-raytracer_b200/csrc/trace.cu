@@ -297,7 +297,8 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
                     new_thresh = mixed ? min(a.refill_threshold, a.refill_incoherent) : a.refill_threshold;
                 }
                 my_ray[0] = make_float2(ox, ix); my_ray[1] = make_float2(oy, iy); my_ray[2] = make_float2(oz, iz);
-                h.t = FLT_MAX; h.slot = -1; sp = 0; tracing = true;
+                // occlusion queries (MODE 0, any_hit): only hits before tmax count, and the first one found ends the ray
+                h.t = (MODE == 0 && a.any_hit) ? a.tmax : FLT_MAX; h.slot = -1; sp = 0; tracing = true;
                 // slab test against the scene box, R/src/CUDAKernels.cu:237-262 (same operation order)
                 bool in = nu > 0;
                 float tMin = __fmul_rn(__fsub_rn(ix < 0.f ? bhi[0] : blo[0], ox), ix);
@@ -313,7 +314,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
                 if (tzmin > tMin) tMin = tzmin;
                 if (tzmax < tMax) tMax = tzmax;
                 if (in) {
-                    rMin = tMin; pMin = fmaxf(tMin, 0.f); pMax = tMax;
+                    rMin = tMin; pMin = fmaxf(tMin, 0.f); pMax = (MODE == 0 && a.any_hit) ? fminf(tMax, h.t) : tMax;
                     // Nu == 1: no internal node; the single leaf starts at slot 0 (and must not be
                     // interval-pruned: the reference tests it unconditionally once the box is hit)
                     if (nu == 1) { cur = BIH_REF_LEAFREF(0); pMin = -FLT_MAX; pMax = FLT_MAX; }
@@ -398,7 +399,8 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
             const char* tp;
             asm("mad.wide.u32 %0, %1, 12, %2;" : "=l"(tp) : "r"(cur & 0x7FFFFFFCu), "l"(tris_b));
             test_leaf<COUNTED>(tp, ox, oy, oz, dx, dy, dz, h, ntris);
-            POP_VALID();
+            if (MODE == 0 && a.any_hit && h.slot >= 0) { sp = 0; cur = NONE; }      // occluded: nothing else to learn
+            else POP_VALID();
         }
 #undef POP_VALID
         __syncwarp();

@@ -134,6 +134,11 @@ BIHRT_API int bihrt_export_reference_view(bihrt_ctx* ctx, bihrt_refview* view); 
  *      prim = input triangle index = tris_indexes[slot].  rays / outputs: host or device; any
  *      output may be NULL. ---------------------------------------------------------------------- */
 BIHRT_API int bihrt_trace(bihrt_ctx* ctx, const bihrt_ray* rays, int64_t n, float* t, int32_t* slot, int32_t* prim);
+/* Occlusion query (shadow rays): blocker[i] = slot of SOME triangle ray i hits with 0 < t < tmax, or -1 (host or
+ * device).  The traversal is cut at tmax and ends at the first such hit, so blocker[i] >= 0 exactly when the closest
+ * hit bihrt_trace reports has t < tmax; which blocker is found is unspecified.  With the shadow rays of
+ * bihrt_secondary_rays (direction = light - origin) tmax = 1 asks "is the light hidden". */
+BIHRT_API int bihrt_trace_any(bihrt_ctx* ctx, const bihrt_ray* rays, int64_t n, float tmax, int32_t* blocker);
 /* instrumented trace: counters[0]=internal nodes visited, [1]=triangle tests, [2]=max stack depth,
  * [3]=rays; same results as bihrt_trace (outputs may be NULL). */
 BIHRT_API int bihrt_trace_counted(bihrt_ctx* ctx, const bihrt_ray* rays, int64_t n, float* t, int32_t* slot,

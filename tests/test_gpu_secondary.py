@@ -53,3 +53,11 @@ def test_secondary_rays(renderer, scenes, oracle, scene):
         np.testing.assert_array_equal(sg.cpu().numpy(), s0)
         np.testing.assert_array_equal(tg.cpu().numpy(), t0)
         np.testing.assert_array_equal(pg.cpu().numpy(), p0)
+        # occlusion query: some hit before tmax <=> the closest hit is before tmax (the light sits at t = 1 on shadow rays)
+        for tmax in (1.0, 0.25, 3.0):
+            blk_d = renderer.trace_any(rays_d, tmax=tmax)
+            renderer.sync()                                   # device outputs are asynchronous on the context's stream
+            blk = blk_d.cpu().numpy()
+            np.testing.assert_array_equal(blk >= 0, (s0 >= 0) & (t0 < np.float32(tmax)))
+            assert blk.max() < len(tri)
+        np.testing.assert_array_equal(renderer.trace_any(rays, tmax=1.0) >= 0, (s0 >= 0) & (t0 < 1.0))      # host buffers
