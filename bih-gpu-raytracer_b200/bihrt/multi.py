@@ -77,19 +77,32 @@ def replicate_bih(renderer, dist, src=0, device=None):
 
 
 def open_peer_framebuffer(renderer, dist, w, h, dst=0, device=None):
-    """Fused gather: rank `dst` shares its w x h framebuffer with the other ranks (CUDA IPC handle, one 64-byte
+    """Fused gather: rank `dst` shares its w x h framebuffer with the other ranks (CUDA IPC handle, one 65-byte
     broadcast); every rank gets the device pointer to hand to Renderer.render_interleaved_to, whose trace kernel
-    then stores the finished pixels straight into rank dst's memory over NVLink.  Returns (pointer, is_peer)."""
+    then stores the finished pixels straight into rank dst's memory over NVLink.  Returns (pointer, is_peer);
+    pointer is None on a rank where the mapping is not available (no exception escapes before or after the
+    broadcast, so the ranks stay in step and can agree on a fall-back)."""
     import torch
     rank = dist.get_rank()
     dev = device if device is not None else "cuda:%d" % renderer.device
-    h64 = torch.zeros(64, dtype=torch.uint8, device=dev)
+    h65 = torch.zeros(65, dtype=torch.uint8)
     if rank == dst:
-        h64.copy_(torch.frombuffer(bytearray(renderer.framebuffer_ipc_export(w, h)), dtype=torch.uint8))
-    dist.broadcast(h64, src=dst)
+        try:
+            h65[:64] = torch.frombuffer(bytearray(renderer.framebuffer_ipc_export(w, h)), dtype=torch.uint8)
+            h65[64] = 1
+        except Exception:       # noqa
+            pass
+    h65 = h65.to(dev)
+    dist.broadcast(h65, src=dst)
+    h65 = h65.cpu()
+    if int(h65[64]) != 1:
+        return None, False
     if rank == dst:
         return renderer.framebuffer_ptr()[0], False
-    return renderer.framebuffer_ipc_open(bytes(h64.cpu().numpy().tobytes())), True
+    try:
+        return renderer.framebuffer_ipc_open(bytes(h65[:64].numpy().tobytes())), True
+    except Exception:           # noqa
+        return None, False
 
 
 def frame_barrier(dist, token):
