@@ -562,7 +562,7 @@ int bihrt_render_interleaved(bihrt_ctx* c, const bihrt_camera* cam, int32_t w, i
 // framebuffer).  A target on another device of this process gets peer access enabled on first use.
 int bihrt_render_interleaved_to(bihrt_ctx* c, const bihrt_camera* cam, int32_t w, int32_t h, int32_t spp, uint64_t seed, uint32_t flags,
                                 int32_t index, int32_t count, uint32_t* target_fb) {
-    if (!c) return BIHRT_ERR_INVALID;
+    ENTER(c);                                 // allocations below must land on this context's device
     if (flags & BIHRT_RENDER_COUNTS) return bihrt_fail(c, BIHRT_ERR_INVALID, "bihrt_render_interleaved_to writes colours, not counts");
     if (target_fb) {
         cudaPointerAttributes at;
@@ -772,6 +772,34 @@ int bihrt_bih_region(bihrt_ctx* c, int64_t n, void** dev_ptr, uint64_t* bytes) {
     *dev_ptr = c->d_blob;
     *bytes = 64 + (uint64_t)std::max<int64_t>(n, 1) * 16 + (uint64_t)n * 48;
     return BIHRT_OK;
+}
+
+int bihrt_bih_adopt(bihrt_ctx* c, int64_t n);
+
+// Same replication inside ONE process (a C host driving several GPUs without NCCL): a peer copy of the region over
+// NVLink, ordered after everything enqueued so far on the source context's stream and before whatever the destination
+// context does next.
+int bihrt_bih_copy(bihrt_ctx* dst, bihrt_ctx* src) {
+    if (!dst || !src) return BIHRT_ERR_INVALID;
+    if (dst == src) return BIHRT_OK;
+    if (!src->built) return bihrt_fail(dst, BIHRT_ERR_STATE, "source BIH not built");
+    void* p = nullptr; uint64_t bytes = 0;
+    int rc = bihrt_bih_region(dst, src->n, &p, &bytes);          // sets the destination device
+    if (rc) return rc;
+    if (dst->device != src->device) {
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, dst->device, src->device);
+        if (can) { cudaError_t e = cudaDeviceEnablePeerAccess(src->device, 0); if (e != cudaSuccess) cudaGetLastError(); }
+    }
+    cudaEvent_t ev = nullptr;
+    BIHRT_CUDA(dst, cudaSetDevice(src->device));
+    BIHRT_CUDA(dst, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    BIHRT_CUDA(dst, cudaEventRecord(ev, src->stream));
+    BIHRT_CUDA(dst, cudaSetDevice(dst->device));
+    BIHRT_CUDA(dst, cudaStreamWaitEvent(dst->stream, ev, 0));
+    BIHRT_CUDA(dst, cudaMemcpyPeerAsync(dst->d_blob, dst->device, src->d_blob, src->device, (size_t)bytes, dst->stream));
+    cudaEventDestroy(ev);                                        // released once the recorded work has completed
+    return bihrt_bih_adopt(dst, src->n);
 }
 
 int bihrt_bih_adopt(bihrt_ctx* c, int64_t n) {

@@ -7,8 +7,13 @@
  * with the reference's camera, resolution and samples per pixel; the packed framebuffer is written as a
  * PPM instead of being presented through OpenGL (R/src/Renderer.cpp:644-670).
  *
- *   bihrt_cli <mesh.obj | mesh.tri9> [-w 640] [-h 480] [-s 4] [-f frames] [-o out.ppm] [-d device]
+ *   bihrt_cli <mesh.obj | mesh.tri9> [-w 640] [-h 480] [-s 4] [-f frames] [-o out.ppm] [-d device] [-g gpus]
  *   (.tri9 = raw little-endian float32, 9 floats per triangle)
+ *
+ * -g N (N = 2, 4, 8): devices device .. device+N-1 of this process share the frame.  Device `device`
+ * rebuilds the BIH, the others receive it by a peer copy over NVLink (bihrt_bih_copy), every device traces every
+ * N-th run of 32-ray units of every tile and its trace kernel stores the finished pixels straight into the first
+ * device's framebuffer (bihrt_render_interleaved_to): no reduce, no second framebuffer.
  */
 #define _POSIX_C_SOURCE 200809L
 #include <stdint.h>
@@ -30,7 +35,7 @@ static double now_ms(void) {
 
 int main(int argc, char** argv) {
     const char* path = NULL; const char* out = "frame.ppm";
-    int w = 640, h = 480, spp = 4, frames = 1, device = 0;     /* R/src/Constants.h:4-8 */
+    int w = 640, h = 480, spp = 4, frames = 1, device = 0, gpus = 1;     /* R/src/Constants.h:4-8 */
     for (int i = 1; i < argc; i++) {
         if (!strcmp(argv[i], "-w") && i + 1 < argc) w = atoi(argv[++i]);
         else if (!strcmp(argv[i], "-h") && i + 1 < argc) h = atoi(argv[++i]);
@@ -38,9 +43,11 @@ int main(int argc, char** argv) {
         else if (!strcmp(argv[i], "-f") && i + 1 < argc) frames = atoi(argv[++i]);
         else if (!strcmp(argv[i], "-o") && i + 1 < argc) out = argv[++i];
         else if (!strcmp(argv[i], "-d") && i + 1 < argc) device = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "-g") && i + 1 < argc) gpus = atoi(argv[++i]);
         else path = argv[i];
     }
-    if (!path) { fprintf(stderr, "usage: %s <mesh.obj|mesh.tri9> [-w W] [-h H] [-s spp] [-f frames] [-o out.ppm] [-d dev]\n", argv[0]); return 2; }
+    if (!path) { fprintf(stderr, "usage: %s <mesh.obj|mesh.tri9> [-w W] [-h H] [-s spp] [-f frames] [-o out.ppm] [-d dev] [-g gpus]\n", argv[0]); return 2; }
+    if (gpus < 1 || gpus > 16) { fprintf(stderr, "-g must be 1..16\n"); return 2; }
 
     bihrt_ctx* ctx = NULL;
     bihrt_config cfg; memset(&cfg, 0, sizeof cfg); cfg.device = device;
@@ -65,11 +72,33 @@ int main(int argc, char** argv) {
     const float aspect = (float)w / (float)h;
     bihrt_camera cam = { { 2.0f, 0.0f, -2.0f }, { 0.0f, -1.0f, -1.0f }, { aspect * 2.0f, 0.0f, 0.0f }, { 0.0f, 2.0f, 0.0f } };
 
+    /* helper contexts on the other devices (-g N) */
+    bihrt_ctx* helper[16] = { NULL };
+    for (int g = 1; g < gpus; g++) {
+        bihrt_config hc; memset(&hc, 0, sizeof hc); hc.device = device + g;
+        int rc = bihrt_create(&helper[g], &hc);
+        if (rc != BIHRT_OK) { fprintf(stderr, "bihrt_create(device %d) -> %d\n", device + g, rc); for (int k = 1; k < g; k++) bihrt_destroy(helper[k]); bihrt_destroy(ctx); return 1; }
+    }
+#define CHECKH(g, call) do { int rc_ = (call); if (rc_ != BIHRT_OK) { \
+    fprintf(stderr, "device %d: %s -> %d: %s\n", device + (g), #call, rc_, bihrt_last_error(helper[g])); \
+    for (int k_ = 1; k_ < gpus; k_++) { bihrt_destroy(helper[k_]); } \
+    bihrt_destroy(ctx); return 1; } } while (0)
+
     bihrt_build_info info;
     for (int f = 0; f < frames; f++) {                         /* the reference rebuilds every frame */
         double t0 = now_ms();
         CHECK(bihrt_build(ctx));
-        CHECK(bihrt_render(ctx, &cam, w, h, spp, 1984u + (uint64_t)f, BIHRT_RENDER_JITTER));
+        if (gpus == 1) {
+            CHECK(bihrt_render(ctx, &cam, w, h, spp, 1984u + (uint64_t)f, BIHRT_RENDER_JITTER));
+        } else {
+            uint32_t* fb0 = NULL;
+            for (int g = 1; g < gpus; g++) CHECKH(g, bihrt_bih_copy(helper[g], ctx));      /* waits for the build only */
+            CHECK(bihrt_render_interleaved_to(ctx, &cam, w, h, spp, 1984u + (uint64_t)f, BIHRT_RENDER_JITTER, 0, gpus, NULL));
+            CHECK(bihrt_framebuffer(ctx, &fb0, NULL, NULL));
+            for (int g = 1; g < gpus; g++)
+                CHECKH(g, bihrt_render_interleaved_to(helper[g], &cam, w, h, spp, 1984u + (uint64_t)f, BIHRT_RENDER_JITTER, g, gpus, fb0));
+            for (int g = 1; g < gpus; g++) CHECKH(g, bihrt_sync(helper[g]));
+        }
         CHECK(bihrt_sync(ctx));
         double t1 = now_ms();
         CHECK(bihrt_get_build_info(ctx, &info));
@@ -92,6 +121,7 @@ int main(int argc, char** argv) {
         printf("wrote %s\n", out);
     }
     free(fb);
+    for (int g = 1; g < gpus; g++) bihrt_destroy(helper[g]);
     bihrt_destroy(ctx);
     return 0;
 }

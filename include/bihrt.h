@@ -220,6 +220,9 @@ BIHRT_API int bihrt_bih_import(bihrt_ctx* ctx, const void* dev_src, uint64_t byt
  * receivers call bihrt_bih_adopt(n) once the broadcast has been enqueued on the context's stream. */
 BIHRT_API int bihrt_bih_region(bihrt_ctx* ctx, int64_t n, void** dev_ptr, uint64_t* bytes);
 BIHRT_API int bihrt_bih_adopt(bihrt_ctx* ctx, int64_t n);
+/* The same inside ONE process (a C host driving several GPUs, no NCCL): peer copy of src's BIH into dst over NVLink,
+ * ordered after the work enqueued on src's stream and before dst's next call. */
+BIHRT_API int bihrt_bih_copy(bihrt_ctx* dst, bihrt_ctx* src);
 
 #ifdef __cplusplus
 }

@@ -38,6 +38,25 @@ def test_cli_renders_like_the_library(renderer, scenes, tmp_path):
     assert (img[..., 2] == 0).any() and (img[..., 2] == 40).any()    # both hits (yellow) and misses in the frame
 
 
+@pytest.mark.skipif(not os.path.exists(CLI), reason="bihrt_cli not built")
+def test_cli_two_gpus_render_the_same_frame(scenes, tmp_path):
+    """-g 2: BIH peer-copied to the second device, both trace kernels store into the first device's framebuffer."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    tri = (scenes.displaced_sphere(64) * np.float32(0.8) + np.tile(np.float32([2.4, 0.0, 0.0]), 3)).astype(np.float32)
+    raw = tmp_path / "mesh.tri9"
+    tri.tofile(raw)
+    imgs = []
+    for g in (1, 2):
+        out = tmp_path / ("frame%d.ppm" % g)
+        p = subprocess.run([CLI, str(raw), "-w", "330", "-h", "200", "-s", "4", "-f", "2", "-g", str(g), "-o", str(out)],
+                           capture_output=True, text=True, timeout=120)
+        assert p.returncode == 0, p.stdout + p.stderr
+        imgs.append(read_ppm(out))
+    np.testing.assert_array_equal(imgs[0], imgs[1])
+
+
 def test_cli_reports_errors():
     p = subprocess.run([CLI, "/nonexistent.obj"], capture_output=True, text=True, timeout=60)
     assert p.returncode == 1 and "cannot open" in p.stderr
