@@ -3,18 +3,23 @@
 // Camera::GetRay / Ray::Ray (R/src/Camera.cu:18-20, R/src/Ray.cu:3-10).
 //
 // Kernel shape
-//   * persistent warps (grid = SMs x resident blocks); a warp takes chunks of work items (rays, or
-//     pixels in 8x4-tile order) from one global atomic counter and hands them to its lanes one at a
-//     time: a lane whose ray has ended does not wait for the other 31 -- once `refill_threshold`
-//     lanes are idle (or nobody is busy) they are given their next sample / pixel / ray together;
+//   * persistent warps (grid = SMs x 8 resident blocks of 4 warps); a warp takes units of 32 work items from one
+//     global atomic counter (or from per-SM queues, 1 spp launches of >= 16 M rays).  Camera modes: an item is a
+//     pixel's sample group -- the samples of a pixel sit in CONSECUTIVE LANES, the warp moves from sample to sample
+//     in lock step and a pixel is written once, as its final colour, by the lane that completes it (possibly into
+//     another GPU's framebuffer: bihrt_render_interleaved_to).  Ray lists: lanes whose ray ended are refilled once
+//     `refill_threshold` of them are idle (sooner for packets with mixed direction signs);
+//   * the tiles of a camera frame are traced in the order k_tile_order derived from the PREVIOUS launch of the same
+//     frame geometry (longest unit per tile, expensive tiles first): the launch is as long as its longest unit, and
+//     a unit of silhouette rays is ~0.4 ms of dependent fetches on the 1 M-triangle sphere;
 //   * every lane walks its own ray with a short stack of 16-byte items (child reference + the three
-//     interval bounds) in local memory; a leaf is an item like a node, so the hot loop has one shape;
+//     interval bounds) in local memory; a leaf is an item like a node, so the hot loop has one shape.  An item in
+//     hand is valid by construction; only items popped from the stack are re-checked against the closest hit;
 //   * nodes (16 B) and leaf-ordered triangles (3 x 16 B) are fetched with single 128-bit read-only
 //     loads; the per-axis ray constants (origin, 1/dir) sit in shared memory and are picked with the
 //     node's axis bits by one 64-bit LDS instead of a select chain;
-//   * two-phase ("while-while") loop: lanes step through internal nodes until they hold a leaf, the
-//     warp re-converges, leaves are tested, repeat; a vote ends the node phase early when most lanes
-//     already wait with a leaf.
+//   * two-phase ("while-while") loop: lanes take 3 node steps (unrolled), the warp votes, leaves are tested,
+//     repeat; the vote ends the node phase as soon as the lanes waiting with a leaf outnumber the walking ones.
 //
 // Logical per-ray algorithm = oracle/bih_oracle.c:traverse_proper (pruned traversal that returns what
 // the reference's TraverseTree returns, including on axis-aligned flat geometry where the reference's
