@@ -131,7 +131,7 @@ void bihrt_destroy(bihrt_ctx* c) {
     dev_free(&c->d_umc); dev_free(&c->d_first); dev_free(&c->d_hist); dev_free(&c->d_lookback);
     dev_free(&c->d_heaps); dev_free(&c->d_scenebox_enc);
     dev_free(&c->d_fb); dev_free(&c->d_counters); dev_free(&c->d_work);
-    dev_free(&c->d_tile_cost); dev_free(&c->d_tile_order);
+    for (auto& ts : c->tile_slots) { dev_free(&ts.cost); dev_free(&ts.order); }
     if (c->d_io) { cudaFree(c->d_io); c->d_io = nullptr; }
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -167,7 +167,7 @@ int bihrt_set_option(bihrt_ctx* c, const char* name, int64_t v) {
     }
     else if (!strcmp(name, "trace_lane_groups")) c->opt_lane_groups = (int)v;
     else if (!strcmp(name, "trace_sm_queues")) c->opt_sm_queues = (int)v;
-    else if (!strcmp(name, "trace_tile_order")) { c->opt_tile_order = (int)v; c->tile_order_valid = false; }
+    else if (!strcmp(name, "trace_tile_order")) { c->opt_tile_order = (int)v; for (auto& ts : c->tile_slots) ts.valid = false; }
     else if (!strcmp(name, "interleave_chunk")) c->opt_interleave_chunk = (int)std::max<int64_t>(1, std::min<int64_t>(1024, v));
     else if (!strcmp(name, "trace_vote_wait")) c->opt_vote_wait = (int)v;
     else if (!strcmp(name, "trace_vote_walk")) c->opt_vote_walk = (int)v;

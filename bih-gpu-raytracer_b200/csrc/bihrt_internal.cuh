@@ -96,8 +96,9 @@ struct bihrt_ctx {
     uint32_t* d_work = nullptr;                        // persistent-kernel work counter
     // cost-ordered tiles: the longest unit of every 32x32-pixel tile measured by the previous launch of the same frame
     // geometry, and the tile order (most expensive first) derived from it
-    uint32_t *d_tile_cost = nullptr, *d_tile_order = nullptr; size_t tile_cap = 0;
-    uint64_t  tile_sig = 0; bool tile_order_valid = false;
+    // (a few slots keyed by the launch geometry, so that a frame's camera pass and its shadow / bounce lists each keep theirs)
+    struct TileSlot { uint64_t sig = 0; bool valid = false; uint32_t *cost = nullptr, *order = nullptr; size_t cap = 0; };
+    TileSlot tile_slots[4]; int tile_next = 0;
 
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool        build_timed = false;
@@ -152,7 +153,7 @@ struct TraceArgs {
 };
 int bihrt_trace_launch(bihrt_ctx* c, const TraceArgs& a, int mode /*0 rays,1 render fb,2 render hits*/, bool counted);
 int bihrt_resolve_launch(bihrt_ctx* c, uint32_t* fb, int npix, int spp);
-int bihrt_tile_order_launch(bihrt_ctx* c, uint32_t ntiles);
+int bihrt_tile_order_launch(bihrt_ctx* c, uint32_t* cost, uint32_t* order, uint32_t ntiles);
 // shade.cu
 int bihrt_secondary_launch(bihrt_ctx* c, const float* t, const int32_t* slot, int64_t n, uint32_t* tile_cnt, unsigned long long* total,
                            const bihrt_camera& cam, int w, int h, int spp, uint64_t seed, uint32_t flags, int kind, const float light[3],

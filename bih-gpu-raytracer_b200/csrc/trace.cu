@@ -111,7 +111,8 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
     // work items
     uint64_t total;
     int tx = 1;
-    if (MODE == 0) total = (uint64_t)a.nrays;
+    // ray lists with cost-ordered chunks: the list is dealt in chunks of 1024 rays (the last one padded)
+    if (MODE == 0) total = a.tile_cost ? (((uint64_t)a.nrays + 1023u) >> 10) << 10 : (uint64_t)a.nrays;
     else {
         tx = (a.w + 31) / 32;
         const int ty = (a.h + 31) / 32, T = tx * ty;
@@ -242,10 +243,15 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
                     }
                     base = __shfl_sync(FULL, base, 0);
                     got = __shfl_sync(FULL, got, 0);
+                    if (MODE == 0 && a.tile_cost && unit_tile != 0xFFFFFFFFu) {
+                        // ray lists: the time between two fetches of the warp is charged to the chunk of the earlier one
+                        if (lane == 0) atomicMax(a.tile_cost + unit_tile, (uint32_t)min((unsigned long long)(clock64() - unit_t0) >> 8, 0xFFFFFFFFull));
+                        unit_tile = 0xFFFFFFFFu;
+                    }
                     if (base == ~0ull) { exhausted = true; break; }
                     pool_next = base;
                     pool_end = min(base + got, total);
-                    if (MODE != 0 && a.tile_cost && unit_tile == 0xFFFFFFFFu) {
+                    if (a.tile_cost && unit_tile == 0xFFFFFFFFu) {
                         const uint32_t m = (uint32_t)(base >> (10 + gshift));
                         unit_tile = a.tile_order ? __ldg(a.tile_order + m) : m;
                         unit_t0 = clock64();
@@ -256,6 +262,13 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
                 const bool served = want_item && (uint64_t)rank < avail;
                 if (served) {
                     item = pool_next + rank; s = 0; hits = 0; want_item = false;
+                    if (MODE == 0 && a.tile_cost) {
+                        // logical item -> ray: chunk (item >> 10) is the chunk traced m-th in cost order
+                        const uint32_t mi = (uint32_t)(item >> 10);
+                        const uint64_t ray = ((uint64_t)(a.tile_order ? __ldg(a.tile_order + mi) : mi) << 10) | (item & 1023u);
+                        item = ray < (uint64_t)a.nrays ? ray : ~0ull;        // padding of the last chunk
+                        if (item == ~0ull) want_item = true;
+                    }
                     if (MODE != 0) {
                         const uint64_t pix = item >> gshift;
                         s0 = a.s_begin + (int)((uint32_t)item & ((1u << gshift) - 1u)) * nsamp;
@@ -496,8 +509,8 @@ __global__ void __launch_bounds__(1024) k_tile_order(uint32_t* __restrict__ cost
     for (uint32_t i = i0; i < i1; i++) cost[i] = 0;
 }
 
-int bihrt_tile_order_launch(bihrt_ctx* c, uint32_t ntiles) {
-    k_tile_order<<<1, 1024, 0, c->stream>>>(c->d_tile_cost, c->d_tile_order, ntiles);
+int bihrt_tile_order_launch(bihrt_ctx* c, uint32_t* cost, uint32_t* order, uint32_t ntiles) {
+    k_tile_order<<<1, 1024, 0, c->stream>>>(cost, order, ntiles);
     c->kernel_launches += 1;
     BIHRT_CUDA(c, cudaGetLastError());
     return BIHRT_OK;
@@ -537,29 +550,45 @@ int bihrt_trace_launch(bihrt_ctx* c, const TraceArgs& a_in, int mode, bool count
     // cost-ordered tiles (camera modes, one global counter): reuse the order measured by the previous launch of the same
     // frame geometry; always record the costs of this one
     uint32_t ntiles = 0;
+    uint64_t sig = 0;
     // (launches of tens of milliseconds have no tail to speak of and lose ~0.5 % to the changed tile neighbourhood; tiny
     // scenes have no long units -- the Cornell box frame is 25 us -- and only pay for the extra k_tile_order launch)
-    if (mode != 0 && a.queues == 1 && (c->opt_tile_order > 1 || (c->opt_tile_order == 1 && rays >= (64ll << 10) && rays < (48ll << 20) && c->n >= 10000))) {
-        const int tx = (a.w + 31) / 32, ty = (a.h + 31) / 32, T = tx * ty;
-        const int mine = T > a.shard_index ? (T - a.shard_index + a.shard_count - 1) / a.shard_count : 0;
-        if (mine > 1 && mine <= 65536) {
-            ntiles = (uint32_t)mine;
-            if ((size_t)ntiles > c->tile_cap) {
-                if (c->d_tile_cost) cudaFree(c->d_tile_cost);
-                if (c->d_tile_order) cudaFree(c->d_tile_order);
-                c->d_tile_cost = c->d_tile_order = nullptr; c->tile_cap = 0; c->tile_order_valid = false;
-                if (cudaMalloc(&c->d_tile_cost, (size_t)ntiles * 4) != cudaSuccess || cudaMalloc(&c->d_tile_order, (size_t)ntiles * 4) != cudaSuccess) {
-                    cudaGetLastError(); ntiles = 0;
-                } else c->tile_cap = ntiles;
-            }
+    const bool order_on = a.queues == 1 && (c->opt_tile_order > 1 || (c->opt_tile_order == 1 && rays >= (64ll << 10) && rays < (48ll << 20) && c->n >= 10000));
+    if (order_on) {
+        if (mode == 0) {
+            // ray lists: chunks of 1024 rays play the role of tiles; the order is reused for lists of the same length (the
+            // next frame's shadow / bounce batch), stale costs only change the schedule, never a result
+            if (a.nrays > 1024 && a.nrays <= (65536ll << 10)) { ntiles = (uint32_t)((a.nrays + 1023) >> 10); sig = (1ull << 63) | (uint64_t)a.nrays; }
+        } else {
+            const int tx = (a.w + 31) / 32, ty = (a.h + 31) / 32, T = tx * ty;
+            const int mine = T > a.shard_index ? (T - a.shard_index + a.shard_count - 1) / a.shard_count : 0;
+            if (mine > 1 && mine <= 65536) ntiles = (uint32_t)mine;
+            sig = ((uint64_t)a.w << 48) ^ ((uint64_t)a.h << 32) ^ ((uint64_t)a.gshift << 28) ^ ((uint64_t)a.shard_index << 20) ^
+                  ((uint64_t)a.shard_count << 12) ^ ((uint64_t)a.il_index << 6) ^ (uint64_t)a.il_count ^ ((uint64_t)((a.s_end - a.s_begin) & 0x7f) << 56);
         }
-        if (ntiles) {
-            const uint64_t sig = ((uint64_t)a.w << 48) ^ ((uint64_t)a.h << 32) ^ ((uint64_t)a.gshift << 28) ^ ((uint64_t)a.shard_index << 20) ^
-                                 ((uint64_t)a.shard_count << 12) ^ ((uint64_t)a.il_index << 6) ^ (uint64_t)a.il_count ^ ((uint64_t)(a.s_end - a.s_begin) << 56);
-            if (sig != c->tile_sig) { c->tile_sig = sig; c->tile_order_valid = false; }
-            if (!c->tile_order_valid) BIHRT_CUDA(c, cudaMemsetAsync(c->d_tile_cost, 0, (size_t)ntiles * 4, c->stream));
-            a.tile_cost = c->d_tile_cost;
-            a.tile_order = c->tile_order_valid ? c->d_tile_order : nullptr;
+    }
+    bihrt_ctx::TileSlot* slot = nullptr;
+    if (ntiles) {
+        for (auto& ts : c->tile_slots) if (ts.cap && ts.sig == sig) slot = &ts;
+        if (!slot) {                                  // take the next slot round-robin
+            slot = &c->tile_slots[c->tile_next];
+            c->tile_next = (c->tile_next + 1) % 4;
+            slot->sig = sig; slot->valid = false;
+        }
+        if ((size_t)ntiles > slot->cap) {
+            if (slot->cost) cudaFree(slot->cost);
+            if (slot->order) cudaFree(slot->order);
+            slot->cost = slot->order = nullptr; slot->cap = 0; slot->valid = false;
+            if (cudaMalloc(&slot->cost, (size_t)ntiles * 4) != cudaSuccess || cudaMalloc(&slot->order, (size_t)ntiles * 4) != cudaSuccess) {
+                cudaGetLastError();
+                if (slot->cost) { cudaFree(slot->cost); slot->cost = nullptr; }
+                slot = nullptr; ntiles = 0;
+            } else slot->cap = ntiles;
+        }
+        if (slot) {
+            if (!slot->valid) BIHRT_CUDA(c, cudaMemsetAsync(slot->cost, 0, (size_t)ntiles * 4, c->stream));
+            a.tile_cost = slot->cost;
+            a.tile_order = slot->valid ? slot->order : nullptr;
         }
     }
     const bool shipped = a.vote_wait != 0 && a.vote_walk == TRACE_WALK;    // the unrolled instantiation
@@ -573,8 +602,8 @@ int bihrt_trace_launch(bihrt_ctx* c, const TraceArgs& a_in, int mode, bool count
         case 5: rc = launch<2, true, 0>(c, a); break;
         default: return bihrt_fail(c, BIHRT_ERR_INVALID, "bad trace mode %d", mode);
     }
-    if (rc == BIHRT_OK && ntiles) {
-        if ((rc = bihrt_tile_order_launch(c, ntiles)) == BIHRT_OK) c->tile_order_valid = true;
+    if (rc == BIHRT_OK && slot) {
+        if ((rc = bihrt_tile_order_launch(c, slot->cost, slot->order, ntiles)) == BIHRT_OK) slot->valid = true;
     }
     return rc;
 }

@@ -236,6 +236,12 @@ def test_cost_ordered_tiles_do_not_change_the_frame(scenes, oracle, spp):
             tt, ss, _ = r.render_hits(cam, w, h, spp=spp, jitter=True)
             np.testing.assert_array_equal(ss, s0)
             np.testing.assert_array_equal(tt, t0)
+            # ray lists are dealt in cost-ordered chunks of 1024 rays (the last one padded): same contract
+            tl, sl, pl = r.trace(rays)
+            np.testing.assert_array_equal(sl, s0)
+            np.testing.assert_array_equal(tl, t0)
+            np.testing.assert_array_equal(pl >= 0, s0 >= 0)
+            np.testing.assert_array_equal(r.trace_any(rays, tmax=2.5) >= 0, (s0 >= 0) & (t0 < 2.5))
     r.close()
 
 
