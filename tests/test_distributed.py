@@ -60,6 +60,21 @@ class FakeRenderer:
     def bih_adopt(self, n):
         self.adopted = n
 
+    # fused gather set-up: rank 0 exports a 64-byte handle, the others open it
+    ipc_fails = False
+
+    def framebuffer_ipc_export(self, w, h):
+        if self.ipc_fails:
+            raise RuntimeError("no IPC here")
+        return bytes((7 * i + w + h) % 256 for i in range(64))
+
+    def framebuffer_ptr(self):
+        return 0xF00D, 0, 0
+
+    def framebuffer_ipc_open(self, handle):
+        self.opened = bytes(handle)
+        return 0xBEEF
+
 
 def _worker(rank, world, port, q):
     import torch
@@ -78,6 +93,13 @@ def _worker(rank, world, port, q):
         tok = torch.ones(1, dtype=torch.int32)
         multi.frame_barrier(dist, tok)
         ok_blob = ok_blob and int(tok.item()) == world
+        # fused-gather set-up: every rank ends up with a pointer (own / peer), or all agree there is none
+        ptr, is_peer = multi.open_peer_framebuffer(r, dist, 40, 30, dst=0, device="cpu")
+        ok_blob = ok_blob and ((rank == 0 and (ptr, is_peer) == (0xF00D, False)) or
+                               (rank == 1 and (ptr, is_peer) == (0xBEEF, True) and r.opened == bytes((7 * i + 70) % 256 for i in range(64))))
+        r.ipc_fails = True
+        ptr, is_peer = multi.open_peer_framebuffer(r, dist, 40, 30, dst=0, device="cpu")
+        ok_blob = ok_blob and ptr is None and not is_peer
         # framebuffer gather: each rank holds its own tiles of a known image, 0 elsewhere
         w, h = 200, 120
         full = (np.arange(w * h, dtype=np.int32).reshape(h, w) % 9973) + 1
