@@ -253,3 +253,15 @@ def look_at_camera(eye, target, half, aspect):
     ver = 2 * half * u
     llc = eye + f - 0.5 * hor - 0.5 * ver
     return np.concatenate([eye, llc, hor, ver]).astype(np.float32)
+
+
+def camera_rays(cam12, w, h):
+    """(w*h, 6) float32 pixel-centre primary rays of a 12-float camera (origin, lower-left, horizontal, vertical), row 0 =
+    bottom, the reference's GetRay formula (R/src/Camera.cu:18-20).  For the tools; the tests use the oracle's generator."""
+    cam = np.asarray(cam12, np.float32)
+    u = ((np.arange(w, dtype=np.float32) + np.float32(0.5)) / np.float32(w))[None, :, None]
+    v = ((np.arange(h, dtype=np.float32) + np.float32(0.5)) / np.float32(h))[:, None, None]
+    d = (cam[3:6] + u * cam[6:9] + v * cam[9:12] - cam[0:3]).astype(np.float32).reshape(-1, 3)
+    o = np.broadcast_to(cam[0:3], d.shape)
+    return np.ascontiguousarray(np.concatenate([o, d], 1), dtype=np.float32)
+

@@ -73,8 +73,7 @@ def main():
             print("        render %dx%d spp=%d: min %.3f ms med %.3f ms -> %.1f Mrays/s (min) %.1f (med)" % (
                 a.w, a.h, spp, tt.min(), np.median(tt), nr / tt.min() / 1e3, nr / np.median(tt) / 1e3), flush=True)
         # counters on a 1/16 sample of the primary rays
-        from oracle import oracle as O
-        rays = O.camera_rays(c, a.w // 4, a.h // 4)
+        rays = scenes.camera_rays(c, a.w // 4, a.h // 4)
         _, s, _, cnt = r.trace(rays, counted=True)
         print("        per ray: nodes %.1f tris %.1f max_stack %d hit %.3f" % (
             cnt["nodes"] / len(rays), cnt["tris"] / len(rays), cnt["max_stack"], (s >= 0).mean()), flush=True)

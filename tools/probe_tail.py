@@ -5,14 +5,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "bih-gpu-raytracer_b200"))
 import bihrt
 from bihrt import scenes
-from oracle import oracle as O
 st = torch.cuda.Stream()
 r = bihrt.Renderer(0, stream=st.cuda_stream)
 tri = scenes.displaced_sphere(scenes.SPHERE_NSEG["1m"])
 r.load_models(torch.from_numpy(tri).cuda()).build(); r.sync()
 w, h = 480, 270
 cam = scenes.pinhole_camera(aspect=w / h)
-rays = O.camera_rays(cam, w, h)
+rays = scenes.camera_rays(cam, w, h)
 def timed(fn, reps=7):
     ts = []
     for _ in range(reps):

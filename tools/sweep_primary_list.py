@@ -5,13 +5,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "bih-gpu-raytracer_b200"))
 import bihrt
 from bihrt import scenes
-from oracle import oracle as O
 st = torch.cuda.Stream(); r = bihrt.Renderer(0, stream=st.cuda_stream)
 key = sys.argv[1] if len(sys.argv) > 1 else "1m"
 tri = scenes.displaced_sphere(scenes.SPHERE_NSEG[key]); cam = scenes.pinhole_camera(aspect=1920 / 1080)
 r.load_models(torch.from_numpy(tri).cuda()).build(); r.sync()
 W, H = 1920, 1080
-rays = O.camera_rays(cam, W, H)                      # row-major pixel order
+rays = scenes.camera_rays(cam, W, H)                      # row-major pixel order
 # tile order (8x4 tiles inside 32x32 tiles), like the render kernel walks pixels
 idx = np.arange(W * H).reshape(H, W)
 def tiled(a, th, tw):
