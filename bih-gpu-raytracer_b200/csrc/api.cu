@@ -167,6 +167,7 @@ int bihrt_set_option(bihrt_ctx* c, const char* name, int64_t v) {
     }
     else if (!strcmp(name, "trace_lane_groups")) c->opt_lane_groups = (int)v;
     else if (!strcmp(name, "trace_sm_queues")) c->opt_sm_queues = (int)v;
+    else if (!strcmp(name, "trace_tile_sort_below")) c->opt_tile_sort_below = v;
     else if (!strcmp(name, "trace_tile_order")) { c->opt_tile_order = (int)v; for (auto& ts : c->tile_slots) ts.valid = false; }
     else if (!strcmp(name, "interleave_chunk")) c->opt_interleave_chunk = (int)std::max<int64_t>(1, std::min<int64_t>(1024, v));
     else if (!strcmp(name, "trace_vote_wait")) c->opt_vote_wait = (int)v;

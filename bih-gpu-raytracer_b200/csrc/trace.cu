@@ -509,8 +509,25 @@ __global__ void __launch_bounds__(1024) k_tile_order(uint32_t* __restrict__ cost
     for (uint32_t i = i0; i < i1; i++) cost[i] = 0;
 }
 
-int bihrt_tile_order_launch(bihrt_ctx* c, uint32_t* cost, uint32_t* order, uint32_t ntiles) {
-    k_tile_order<<<1, 1024, 0, c->stream>>>(cost, order, ntiles);
+// Small launches (a few million rays: every tile holds only a handful of units per warp, and the tail is a large part of
+// the launch) get a full descending sort by cost instead: counting sort over 256 buckets of ~2 us, order inside a bucket
+// arbitrary.  480x270 x 16 spp: 2630 -> 3000 Mrays/s; at 33 M rays the same sort loses 3 % to the scattered tiles.
+__global__ void __launch_bounds__(1024) k_tile_sort(uint32_t* __restrict__ cost, uint32_t* __restrict__ order, uint32_t ntiles) {
+    __shared__ uint32_t s_cnt[256], s_off[256];
+    if (threadIdx.x < 256) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < ntiles; i += 1024) atomicAdd(&s_cnt[min(255u, cost[i] >> 4)], 1u);
+    __syncthreads();
+    if (threadIdx.x == 0) { uint32_t run = 0; for (int b = 255; b >= 0; b--) { s_off[b] = run; run += s_cnt[b]; } }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < ntiles; i += 1024) order[atomicAdd(&s_off[min(255u, cost[i] >> 4)], 1u)] = i;
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < ntiles; i += 1024) cost[i] = 0;
+}
+
+int bihrt_tile_order_launch(bihrt_ctx* c, uint32_t* cost, uint32_t* order, uint32_t ntiles, bool full_sort) {
+    if (full_sort) k_tile_sort<<<1, 1024, 0, c->stream>>>(cost, order, ntiles);
+    else k_tile_order<<<1, 1024, 0, c->stream>>>(cost, order, ntiles);
     c->kernel_launches += 1;
     BIHRT_CUDA(c, cudaGetLastError());
     return BIHRT_OK;
@@ -603,7 +620,7 @@ int bihrt_trace_launch(bihrt_ctx* c, const TraceArgs& a_in, int mode, bool count
         default: return bihrt_fail(c, BIHRT_ERR_INVALID, "bad trace mode %d", mode);
     }
     if (rc == BIHRT_OK && slot) {
-        if ((rc = bihrt_tile_order_launch(c, slot->cost, slot->order, ntiles)) == BIHRT_OK) slot->valid = true;
+        if ((rc = bihrt_tile_order_launch(c, slot->cost, slot->order, ntiles, rays < c->opt_tile_sort_below)) == BIHRT_OK) slot->valid = true;
     }
     return rc;
 }
