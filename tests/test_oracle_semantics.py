@@ -115,3 +115,11 @@ def test_camera_rays_and_pack(oracle, scenes):
     fb = oracle.pack_framebuffer(np.array([3, -1, -1, -1], np.int32), 2, 1, 2)
     # pixel 0: one hit one miss -> r=g=(255+20)/2=137.5 -> 137, b=20; pixel 1: miss -> (20,20,40)
     assert fb.tolist() == [(20 << 16) | (137 << 8) | 137, (40 << 16) | (20 << 8) | 20]
+
+
+def test_tool_ray_generator_matches_the_oracle(oracle, scenes):
+    """bihrt.scenes.camera_rays (used by the dev tools, which may not touch oracle/) == the oracle's pixel-centre rays."""
+    for cam, w, h in ((scenes.pinhole_camera(aspect=96 / 54), 96, 54), (scenes.reference_camera(aspect=33 / 17), 33, 17),
+                      (scenes.atrium_camera(64 / 36), 64, 36)):
+        np.testing.assert_array_equal(scenes.camera_rays(cam, w, h), oracle.camera_rays(cam, w, h))
+
