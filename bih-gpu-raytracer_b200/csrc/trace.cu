@@ -540,7 +540,9 @@ int bihrt_resolve_launch(bihrt_ctx* c, uint32_t* fb, int npix, int spp) {
     return BIHRT_OK;
 }
 
+#ifndef TRACE_WALK
 #define TRACE_WALK 3
+#endif
 template <int MODE, bool COUNTED, int WALK>
 static int launch(bihrt_ctx* c, const TraceArgs& a) {
     int per_sm = c->opt_trace_blocks_per_sm;
