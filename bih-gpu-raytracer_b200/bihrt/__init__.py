@@ -62,10 +62,10 @@ class BuildInfo(C.Structure):
 
 # every symbol include/bihrt.h declares (tests check that the library exports all of them)
 ABI_SYMBOLS = [
-    "bihrt_version", "bihrt_create", "bihrt_destroy", "bihrt_last_error", "bihrt_set_stream", "bihrt_sync",
+    "bihrt_version", "bihrt_create", "bihrt_destroy", "bihrt_last_error", "bihrt_set_stream", "bihrt_get_stream", "bihrt_sync",
     "bihrt_set_option", "bihrt_get_stat", "bihrt_scene_load_triangles", "bihrt_scene_update_vertices", "bihrt_scene_load_obj",
     "bihrt_build", "bihrt_refit", "bihrt_get_build_info", "bihrt_export_reference_view", "bihrt_trace", "bihrt_trace_any", "bihrt_trace_counted",
-    "bihrt_render", "bihrt_render_counted", "bihrt_render_shard", "bihrt_render_samples", "bihrt_render_interleaved", "bihrt_render_interleaved_to", "bihrt_framebuffer_ipc_export", "bihrt_framebuffer_ipc_open", "bihrt_framebuffer_ipc_close", "bihrt_bih_region", "bihrt_bih_adopt", "bihrt_bih_copy", "bihrt_framebuffer_resolve", "bihrt_render_hits", "bihrt_secondary_rays", "bihrt_framebuffer", "bihrt_framebuffer_read",
+    "bihrt_render", "bihrt_render_counted", "bihrt_render_shard", "bihrt_render_samples", "bihrt_render_interleaved", "bihrt_render_interleaved_to", "bihrt_framebuffer_ipc_export", "bihrt_framebuffer_ipc_open", "bihrt_framebuffer_ipc_close", "bihrt_framebuffer_ipc_unexport", "bihrt_bih_region", "bihrt_bih_adopt", "bihrt_bih_copy", "bihrt_framebuffer_resolve", "bihrt_render_hits", "bihrt_secondary_rays", "bihrt_framebuffer", "bihrt_framebuffer_read",
     "bihrt_bih_blob_bytes", "bihrt_bih_export", "bihrt_bih_import",
 ]
 
@@ -135,8 +135,42 @@ class Renderer:
             pass
 
     def set_stream(self, cuda_stream):
-        """Run on a caller-owned stream (int handle, e.g. torch.cuda.current_stream().cuda_stream)."""
-        self._check(self._lib.bihrt_set_stream(self._ctx, C.c_void_p(int(cuda_stream) if cuda_stream else 0)))
+        """Run on a caller-owned stream: an int cudaStream_t with CUDA's meaning (0 = the legacy default stream, which is
+        what torch.cuda.current_stream().cuda_stream is on torch's default stream), or None / "own" for the context's
+        private stream."""
+        own = cuda_stream is None or cuda_stream == "own"
+        h = C.c_void_p(-1) if own else C.c_void_p(int(cuda_stream))
+        self._check(self._lib.bihrt_set_stream(self._ctx, h))
+
+    def stream_handle(self):
+        """The cudaStream_t (int) the context launches on."""
+        p = C.c_void_p()
+        self._check(self._lib.bihrt_get_stream(self._ctx, C.byref(p)))
+        return p.value or 0
+
+    # Ordering with torch work.  The library launches on the context's stream; torch tensors handed in were produced,
+    # and tensors handed out will be consumed, on torch's CURRENT stream.  When the two differ they are ordered with
+    # events (no host synchronisation): wait_torch() before a call that reads torch memory, torch_wait() after a call
+    # that wrote it.  Both are no-ops when the context already runs on torch's current stream.
+    def _torch_streams(self):
+        import torch
+        cur = torch.cuda.current_stream(self.device)
+        h = self.stream_handle()
+        if h == cur.cuda_stream:
+            return None, None
+        return torch.cuda.ExternalStream(h, device=self.device), cur
+
+    def wait_torch(self):
+        """The context's stream waits for the work enqueued so far on torch's current stream."""
+        ext, cur = self._torch_streams()
+        if ext is not None:
+            ext.wait_stream(cur)
+
+    def torch_wait(self):
+        """torch's current stream waits for the work enqueued so far on the context's stream."""
+        ext, cur = self._torch_streams()
+        if ext is not None:
+            cur.wait_stream(ext)
 
     def sync(self):
         self._check(self._lib.bihrt_sync(self._ctx))
@@ -162,6 +196,8 @@ class Renderer:
         else:
             n = src.numel() // 9
         self._keep = src
+        if getattr(src, "is_cuda", False):
+            self.wait_torch()
         self._check(self._lib.bihrt_scene_load_triangles(self._ctx, _ptr(src), C.c_int64(n)))
         self.n = n
         return self
@@ -173,6 +209,8 @@ class Renderer:
         else:
             n = src.numel() // 9
         self._keep = src
+        if getattr(src, "is_cuda", False):
+            self.wait_torch()
         self._check(self._lib.bihrt_scene_update_vertices(self._ctx, _ptr(src), C.c_int64(n)))
 
     # -- first half of Renderer::Render -----------------------------------------------------------
@@ -232,11 +270,16 @@ class Renderer:
             t = torch.empty(n, dtype=torch.float32, device=rays.device) if t is None else t
             slot = torch.empty(n, dtype=torch.int32, device=rays.device) if slot is None else slot
             prim = torch.empty(n, dtype=torch.int32, device=rays.device) if prim is None else prim
+        on_dev = any(getattr(x, "is_cuda", False) for x in (rays, t, slot, prim))
+        if on_dev:
+            self.wait_torch()            # rays (and recycled output blocks) were last touched on torch's current stream
         if counted:
             cnt = (C.c_uint64 * 4)()
             self._check(self._lib.bihrt_trace_counted(self._ctx, _ptr(rays), C.c_int64(n), _ptr(t), _ptr(slot), _ptr(prim), cnt))
             return t, slot, prim, {"nodes": cnt[0], "tris": cnt[1], "max_stack": cnt[2], "rays": cnt[3]}
         self._check(self._lib.bihrt_trace(self._ctx, _ptr(rays), C.c_int64(n), _ptr(t), _ptr(slot), _ptr(prim)))
+        if on_dev:
+            self.torch_wait()            # device outputs are written asynchronously on the context's stream
         return t, slot, prim
 
     def trace_any(self, rays, tmax=1.0, blocker=None):
@@ -249,7 +292,12 @@ class Renderer:
             import torch
             n = rays.numel() // 6
             blocker = torch.empty(n, dtype=torch.int32, device=rays.device) if blocker is None else blocker
+        on_dev = any(getattr(x, "is_cuda", False) for x in (rays, blocker))
+        if on_dev:
+            self.wait_torch()
         self._check(self._lib.bihrt_trace_any(self._ctx, _ptr(rays), C.c_int64(n), C.c_float(tmax), _ptr(blocker)))
+        if on_dev:
+            self.torch_wait()
         return blocker
 
     def render(self, camera, w, h, spp=1, seed=1984, jitter=False, shard=(0, 1)):
@@ -299,6 +347,10 @@ class Renderer:
     def framebuffer_ipc_close(self, ptr):
         self._check(self._lib.bihrt_framebuffer_ipc_close(self._ctx, C.c_void_p(ptr)))
 
+    def framebuffer_ipc_unexport(self):
+        """The peers have closed their mappings: the framebuffer may be reallocated again."""
+        self._check(self._lib.bihrt_framebuffer_ipc_unexport(self._ctx))
+
     def framebuffer_resolve(self, spp):
         self._check(self._lib.bihrt_framebuffer_resolve(self._ctx, C.c_int32(spp)))
         return self
@@ -330,6 +382,7 @@ class Renderer:
         src = torch.empty(n, dtype=torch.int32, device=dev)
         cnt = C.c_int64()
         lt = (C.c_float * 3)(*[float(x) for x in light])
+        self.wait_torch()                # the fresh tensors may recycle blocks last used on torch's current stream
         self._check(self._lib.bihrt_secondary_rays(self._ctx, C.byref(cam), C.c_int32(w), C.c_int32(h), C.c_int32(spp), C.c_uint64(seed),
                                                    C.c_uint32(RENDER_JITTER if jitter else 0), C.c_int32({"shadow": 0, "diffuse": 1}[kind]),
                                                    lt, _ptr(rays), _ptr(src), C.byref(cnt)))

@@ -67,10 +67,12 @@ def replicate_bih(renderer, dist, src=0, device=None):
     nbytes = int(size.item())
     blob = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     if rank == src:
+        renderer.wait_torch()
         renderer.bih_export(blob, nbytes)
         renderer.sync()
     dist.broadcast(blob, src=src)
     if rank != src:
+        renderer.wait_torch()            # the import reads the blob the collective wrote on torch's current stream
         renderer.bih_import(blob, nbytes)
         renderer.sync()
     return nbytes
@@ -121,13 +123,29 @@ def replicate_bih_inplace(renderer, dist, n, src=0):
     else:
         ptr, nbytes = renderer.bih_region(n)
         blob = torch.as_tensor(_CudaView(ptr, (nbytes,), "|u1"), device="cuda:%d" % renderer.device)
+    # The collective runs on torch's current stream, the build and the trace on the context's: order them with events
+    # (both are no-ops when the context was given torch's current stream, as bench.py does).
+    renderer.torch_wait()                # the build that wrote the blob / the trace that still reads the old one
     dist.broadcast(blob, src=src)
+    renderer.wait_torch()                # whatever the context does next sees the broadcast blob
     if dist.get_rank() != src:
         renderer.bih_adopt(n)
     return nbytes
 
 
-def gather_framebuffer(fb, dist, dst=0):
-    """Combine the ranks' disjoint shards (0 outside a rank's tiles) on rank `dst`: one reduce."""
+def gather_framebuffer(fb, dist, dst=0, renderer=None):
+    """Combine the ranks' disjoint shards (0 outside a rank's tiles) on rank `dst`: one reduce.  With `renderer` the
+    reduce (torch's current stream) is ordered after the render and before the context's next call."""
+    if renderer is not None:
+        renderer.torch_wait()
     dist.reduce(fb, dst=dst, op=dist.ReduceOp.SUM)
+    if renderer is not None:
+        renderer.wait_torch()
     return fb
+
+
+def frame_barrier_ordered(renderer, dist, token):
+    """frame_barrier for a context that does not run on torch's current stream."""
+    renderer.torch_wait()
+    dist.all_reduce(token)
+    renderer.wait_torch()

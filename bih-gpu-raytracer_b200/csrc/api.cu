@@ -117,6 +117,11 @@ int bihrt_create(bihrt_ctx** out, const bihrt_config* cfg) {
     rc |= dev_alloc(c, &c->d_scenebox_enc, 8);
     rc |= dev_alloc(c, &c->d_counters, 8);
     rc |= dev_alloc(c, &c->d_work, 1024);
+    // hdr->status of the last build, mirrored by the build's last kernel into mapped host memory: the host can look at it
+    // without a copy or a synchronisation of its own
+    if (cudaHostAlloc((void**)&c->h_status, 64, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess ||
+        cudaHostGetDevicePointer((void**)&c->d_status_map, c->h_status, 0) != cudaSuccess) { cudaGetLastError(); rc |= 1; }
+    else *c->h_status = 0;
     if (rc) { bihrt_destroy(c); return BIHRT_ERR_NOMEM; }
     *out = c;
     return BIHRT_OK;
@@ -133,6 +138,7 @@ void bihrt_destroy(bihrt_ctx* c) {
     dev_free(&c->d_fb); dev_free(&c->d_counters); dev_free(&c->d_work);
     for (auto& ts : c->tile_slots) { dev_free(&ts.cost); dev_free(&ts.order); }
     if (c->d_io) { cudaFree(c->d_io); c->d_io = nullptr; }
+    if (c->h_status) { cudaFreeHost(c->h_status); c->h_status = nullptr; }
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->build_graph_exec) cudaGraphExecDestroy(c->build_graph_exec);
@@ -143,17 +149,33 @@ void bihrt_destroy(bihrt_ctx* c) {
 
 const char* bihrt_last_error(const bihrt_ctx* c) { return c ? c->err.c_str() : "null context"; }
 
+// The handle means what it means to every CUDA call: 0 is the legacy default stream (what
+// torch.cuda.current_stream().cuda_stream is when torch runs on its default stream), BIHRT_STREAM_OWN the context's
+// private non-blocking stream.
 int bihrt_set_stream(bihrt_ctx* c, void* s) {
     ENTER(c);
     BIHRT_CUDA(c, cudaStreamSynchronize(c->stream));
-    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    c->stream = (s == BIHRT_STREAM_OWN) ? c->own_stream : (cudaStream_t)s;
+    return BIHRT_OK;
+}
+
+int bihrt_get_stream(bihrt_ctx* c, void** s) {
+    if (!c || !s) return BIHRT_ERR_INVALID;
+    *s = (void*)c->stream;
+    return BIHRT_OK;
+}
+
+// the device watchdog of the last build that has COMPLETED (never blocks)
+static int check_status(bihrt_ctx* c) {
+    const uint32_t st = c->h_status ? *(volatile uint32_t*)c->h_status : 0u;
+    if (st) return bihrt_fail(c, BIHRT_ERR_INTERNAL, "device watchdog tripped during build (status %u): the BIH is invalid, rebuild", st);
     return BIHRT_OK;
 }
 
 int bihrt_sync(bihrt_ctx* c) {
     ENTER(c);
     BIHRT_CUDA(c, cudaStreamSynchronize(c->stream));
-    return BIHRT_OK;
+    return check_status(c);
 }
 
 int bihrt_set_option(bihrt_ctx* c, const char* name, int64_t v) {
@@ -161,7 +183,12 @@ int bihrt_set_option(bihrt_ctx* c, const char* name, int64_t v) {
     if (!strcmp(name, "trace_blocks_per_sm")) c->opt_trace_blocks_per_sm = (int)v;
     else if (!strcmp(name, "trace_refill_threshold")) c->opt_refill_threshold = (int)std::max<int64_t>(1, std::min<int64_t>(32, v));
     else if (!strcmp(name, "build_graph")) c->opt_build_graph = (int)v;
+    else if (!strcmp(name, "debug_trip_watchdog")) {
+        c->opt_debug_trip_watchdog = (int)v;
+        if (c->build_graph_exec) { cudaGraphExecDestroy(c->build_graph_exec); c->build_graph_exec = nullptr; }    // the value is a kernel argument
+    }
     else if (!strcmp(name, "profile")) {
+        BIHRT_CUDA(c, cudaSetDevice(c->device));          // the events belong to this context's device
         c->opt_profile = (int)v;
         if (v) for (int i = 0; i < BIHRT_PROF_EVENTS; i++) if (!c->prof_ev[i]) cudaEventCreate(&c->prof_ev[i]);
     }
@@ -181,6 +208,16 @@ int bihrt_set_option(bihrt_ctx* c, const char* name, int64_t v) {
 int bihrt_get_stat(bihrt_ctx* c, const char* name, int64_t* v) {
     if (!c || !name || !v) return BIHRT_ERR_INVALID;
     if (!strcmp(name, "kernel_launches")) *v = c->kernel_launches;
+    else if (!strcmp(name, "sm_count")) *v = c->sm_count;
+    else if (!strcmp(name, "trace_warp_node_steps") || !strcmp(name, "trace_warp_leaf_steps")) {
+        // of the last instrumented launch (bihrt_trace_counted / bihrt_render_counted): how often a WARP executed the node
+        // step / the triangle test; lane-level counts (counters[0], [1]) / 32 / these = SIMD efficiency of the two phases
+        unsigned long long h[2];
+        BIHRT_CUDA(c, cudaSetDevice(c->device));
+        BIHRT_CUDA(c, cudaMemcpyAsync(h, c->d_counters + 4, 16, cudaMemcpyDeviceToHost, c->stream));
+        BIHRT_CUDA(c, cudaStreamSynchronize(c->stream));
+        *v = (int64_t)h[name[11] == 'n' ? 0 : 1];
+    }
     else if (!strncmp(name, "build_stage_ns_", 15)) {
         // stages: 0 init+memsets, 1 scene_box, 2 morton, 3-6 sort passes, 7 rle, 8 reorder + slot boxes, 9 upper heap levels, 10 nodes
         const int i = atoi(name + 15);
@@ -277,7 +314,9 @@ int bihrt_build(bihrt_ctx* c) {
     BIHRT_CUDA(c, cudaEventRecord(c->ev0, c->stream));
     if (c->n == 0) {
         BIHRT_CUDA(c, cudaMemsetAsync(c->d_hdr, 0, sizeof(BihHeader), c->stream));
-    } else if (c->opt_build_graph && !c->opt_profile) {
+        BIHRT_CUDA(c, cudaStreamSynchronize(c->stream));
+        *c->h_status = 0;
+    } else if (c->opt_build_graph && !c->opt_profile && c->stream != nullptr && c->stream != cudaStreamLegacy) {    // (the legacy stream cannot be captured)
         // The build is ~16 short launches with fixed arguments for a given triangle count: capture them once
         // into a CUDA graph and replay it (the reference rebuilds every frame, R/src/Renderer.cpp:415-503).
         if (!c->build_graph_exec || c->build_graph_n != c->n) {
@@ -429,11 +468,16 @@ static int stage_outputs(bihrt_ctx* c, int64_t n, size_t front_bytes, float* t, 
 }
 
 static int unstage_outputs(bihrt_ctx* c, int64_t n, const OutStage& o) {
-    bool any = false;
-    if (o.ht) { BIHRT_CUDA(c, cudaMemcpyAsync(o.ht, o.t, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream)); any = true; }
-    if (o.hslot) { BIHRT_CUDA(c, cudaMemcpyAsync(o.hslot, o.slot, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream)); any = true; }
-    if (o.hprim) { BIHRT_CUDA(c, cudaMemcpyAsync(o.hprim, o.prim, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream)); any = true; }
-    if (any) BIHRT_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (!o.ht && !o.hslot && !o.hprim) return BIHRT_OK;
+    // host outputs: the call is synchronous anyway -- learn first whether the BIH that was traced is valid (a tripped
+    // build watchdog makes the kernel trace nothing), and leave the caller's arrays untouched if it is not
+    BIHRT_CUDA(c, cudaStreamSynchronize(c->stream));
+    int rc = check_status(c);
+    if (rc) return rc;
+    if (o.ht) BIHRT_CUDA(c, cudaMemcpyAsync(o.ht, o.t, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (o.hslot) BIHRT_CUDA(c, cudaMemcpyAsync(o.hslot, o.slot, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (o.hprim) BIHRT_CUDA(c, cudaMemcpyAsync(o.hprim, o.prim, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+    BIHRT_CUDA(c, cudaStreamSynchronize(c->stream));
     return BIHRT_OK;
 }
 
@@ -441,9 +485,10 @@ static int trace_impl(bihrt_ctx* c, const bihrt_ray* rays, int64_t n, float* t, 
                       bool any_hit = false, float tmax = 0.f) {
     ENTER(c);
     if (!c->built) return bihrt_fail(c, BIHRT_ERR_STATE, "BIH not built");
+    { int st = check_status(c); if (st) return st; }
     if (n < 0 || (n > 0 && !rays)) return bihrt_fail(c, BIHRT_ERR_INVALID, "bad ray array");
     if (n >= (1ll << 32) - (1ll << 24)) return bihrt_fail(c, BIHRT_ERR_INVALID, "too many rays in one call (32-bit work counter)");
-    if (counters) BIHRT_CUDA(c, cudaMemsetAsync(c->d_counters, 0, 32, c->stream));
+    if (counters) BIHRT_CUDA(c, cudaMemsetAsync(c->d_counters, 0, 64, c->stream));
     if (n > 0) {
         const bool rays_dev = is_device_ptr(rays);
         OutStage o; uint8_t* front;
@@ -485,10 +530,31 @@ int bihrt_trace_any(bihrt_ctx* c, const bihrt_ray* rays, int64_t n, float tmax, 
 
 static int render_check(bihrt_ctx* c, const bihrt_camera* cam, int w, int h, int spp, int si, int sc) {
     if (!c->built) return bihrt_fail(c, BIHRT_ERR_STATE, "BIH not built");
+    { int st = check_status(c); if (st) return st; }
     if (!cam || w <= 0 || h <= 0 || spp <= 0 || w > 65535 || h > 65535 || (int64_t)w * h >= (1ll << 31) - (1ll << 24))
         return bihrt_fail(c, BIHRT_ERR_INVALID, "bad render arguments");
     if (sc < 1 || si < 0 || si >= sc) return bihrt_fail(c, BIHRT_ERR_INVALID, "bad shard %d of %d", si, sc);
     return BIHRT_OK;
+}
+
+// CreateCUDABuffers, R/src/Renderer.cpp:762-768.  While a CUDA IPC handle of the framebuffer is out (peers hold a mapping
+// of this very allocation and store into it) it must not be reallocated.
+static int ensure_fb(bihrt_ctx* c, size_t px) {
+    if (px <= c->fb_cap) return BIHRT_OK;
+    if (c->fb_exported)
+        return bihrt_fail(c, BIHRT_ERR_STATE, "framebuffer of %zu pixels is exported through CUDA IPC and cannot grow to %zu: "
+                          "bihrt_framebuffer_ipc_unexport first (after the peers have closed their mappings)", c->fb_cap, px);
+    int rc = dev_alloc(c, &c->d_fb, px);
+    if (rc) { c->fb_cap = 0; return rc; }
+    c->fb_cap = px;
+    return BIHRT_OK;
+}
+
+// lane groups are limited by the 32-bit work counter: padded items = tiles x 1024 pixels x groups
+static int fit_gshift(int w, int h, int shard_count, int g) {
+    const uint64_t tiles = ((uint64_t)(w + 31) / 32) * ((uint64_t)(h + 31) / 32) / (uint64_t)(shard_count > 0 ? shard_count : 1) + 1;
+    while (g > 0 && ((tiles * 1024u) << g) >= (1ull << 32) - (1ull << 24)) g--;
+    return g;
 }
 
 // samples of one pixel laid along consecutive lanes: the largest power of two that divides the sample count (<= 32)
@@ -510,14 +576,14 @@ static int render_impl(bihrt_ctx* c, const bihrt_camera* cam, int32_t w, int32_t
     int rc = render_check(c, cam, w, h, spp, shard_index, shard_count);
     if (rc) return rc;
     const size_t px = (size_t)w * h;
-    if (px > c->fb_cap) { if ((rc = dev_alloc(c, &c->d_fb, px))) { c->fb_cap = 0; return rc; } c->fb_cap = px; }   // CreateCUDABuffers, R/src/Renderer.cpp:762-768
+    if ((rc = ensure_fb(c, px))) return rc;
     c->fb_w = w; c->fb_h = h;
     if (shard_count > 1) BIHRT_CUDA(c, cudaMemsetAsync(c->d_fb, 0, px * 4, c->stream));
     TraceArgs a; base_args(c, a);
     a.cam = *cam; a.w = w; a.h = h; a.spp = spp; a.seed = seed; a.flags = flags;
     a.shard_index = shard_index; a.shard_count = shard_count; a.fb = target ? target : c->d_fb;
     a.s_begin = s_begin; a.s_end = s_end;
-    a.gshift = (shard_count > 1) ? 0 : pick_gshift(c, s_end - s_begin);       // tile shards keep "other pixels are 0"
+    a.gshift = (shard_count > 1) ? 0 : fit_gshift(w, h, 1, pick_gshift(c, s_end - s_begin));       // tile shards keep "other pixels are 0"
     a.il_index = il_index; a.il_count = il_count;
     if (il_count > 1) {
         if (il_index < 0 || il_index >= il_count || ((32 << a.gshift) % il_count) != 0)
@@ -535,7 +601,7 @@ static int render_impl(bihrt_ctx* c, const bihrt_camera* cam, int32_t w, int32_t
     if (!target && (atomics || il_count > 1 || s_begin == s_end)) BIHRT_CUDA(c, cudaMemsetAsync(c->d_fb, 0, px * 4, c->stream));
     if (s_begin == s_end) return BIHRT_OK;            // nothing to trace on this rank: all counts are 0
     if (!counters) return bihrt_trace_launch(c, a, 1, false);
-    BIHRT_CUDA(c, cudaMemsetAsync(c->d_counters, 0, 32, c->stream));
+    BIHRT_CUDA(c, cudaMemsetAsync(c->d_counters, 0, 64, c->stream));
     if ((rc = bihrt_trace_launch(c, a, 1, true))) return rc;
     unsigned long long hc[4];
     BIHRT_CUDA(c, cudaMemcpyAsync(hc, c->d_counters, 32, cudaMemcpyDeviceToHost, c->stream));
@@ -582,7 +648,8 @@ int bihrt_render_interleaved_to(bihrt_ctx* c, const bihrt_camera* cam, int32_t w
         }
     } else {
         const size_t px = (size_t)(w > 0 ? w : 0) * (size_t)(h > 0 ? h : 0);
-        if (px > c->fb_cap) { int rc = dev_alloc(c, &c->d_fb, px); if (rc) { c->fb_cap = 0; return rc; } c->fb_cap = px; }
+        int rc = ensure_fb(c, px);
+        if (rc) return rc;
     }
     return render_impl(c, cam, w, h, spp, seed, flags, 0, 1, nullptr, 0, -1, index, count, target_fb ? target_fb : c->d_fb);
 }
@@ -593,11 +660,20 @@ int bihrt_framebuffer_ipc_export(bihrt_ctx* c, int32_t w, int32_t h, void* handl
     if (!handle64 || w <= 0 || h <= 0) return BIHRT_ERR_INVALID;
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle is 64 bytes");
     const size_t px = (size_t)w * h;
-    if (px > c->fb_cap) { int rc = dev_alloc(c, &c->d_fb, px); if (rc) { c->fb_cap = 0; return rc; } c->fb_cap = px; }
+    int rc = ensure_fb(c, px);
+    if (rc) return rc;
     c->fb_w = w; c->fb_h = h;
     cudaIpcMemHandle_t hnd;
     BIHRT_CUDA(c, cudaIpcGetMemHandle(&hnd, c->d_fb));
     memcpy(handle64, &hnd, 64);
+    c->fb_exported = true;
+    return BIHRT_OK;
+}
+
+// The peers have closed their mappings: the framebuffer may be reallocated again.
+int bihrt_framebuffer_ipc_unexport(bihrt_ctx* c) {
+    if (!c) return BIHRT_ERR_INVALID;
+    c->fb_exported = false;
     return BIHRT_OK;
 }
 
@@ -647,7 +723,7 @@ int bihrt_render_hits(bihrt_ctx* c, const bihrt_camera* cam, int32_t w, int32_t 
     if ((rc = stage_outputs(c, n, 0, t, slot, prim, o, &front))) return rc;
     TraceArgs a; base_args(c, a);
     a.cam = *cam; a.w = w; a.h = h; a.spp = spp; a.seed = seed; a.flags = flags;
-    a.s_begin = 0; a.s_end = spp; a.gshift = pick_gshift(c, spp);
+    a.s_begin = 0; a.s_end = spp; a.gshift = fit_gshift(w, h, 1, pick_gshift(c, spp));
     a.out_t = o.t; a.out_slot = o.slot; a.out_prim = o.prim;
     if ((rc = bihrt_trace_launch(c, a, 2, false))) return rc;
     return unstage_outputs(c, n, o);
@@ -673,7 +749,7 @@ int bihrt_secondary_rays(bihrt_ctx* c, const bihrt_camera* cam, int32_t w, int32
     uint32_t* d_cnt = (uint32_t*)((uint8_t*)c->d_io + (size_t)n * 8);
     TraceArgs a; base_args(c, a);
     a.cam = *cam; a.w = w; a.h = h; a.spp = spp; a.seed = seed; a.flags = flags;
-    a.s_begin = 0; a.s_end = spp; a.gshift = pick_gshift(c, spp);
+    a.s_begin = 0; a.s_end = spp; a.gshift = fit_gshift(w, h, 1, pick_gshift(c, spp));
     a.out_t = d_t; a.out_slot = d_slot; a.out_prim = nullptr;
     if ((rc = bihrt_trace_launch(c, a, 2, false))) return rc;
     if ((rc = bihrt_secondary_launch(c, d_t, d_slot, n, d_cnt, c->d_counters + 3, *cam, w, h, spp, seed, flags, kind, light, out_rays, out_sample))) return rc;
@@ -700,7 +776,7 @@ int bihrt_framebuffer_read(bihrt_ctx* c, uint32_t* host_dst) {
     if (!host_dst) return BIHRT_ERR_INVALID;
     BIHRT_CUDA(c, cudaMemcpyAsync(host_dst, c->d_fb, (size_t)c->fb_w * c->fb_h * 4, cudaMemcpyDeviceToHost, c->stream));
     BIHRT_CUDA(c, cudaStreamSynchronize(c->stream));
-    return BIHRT_OK;
+    return check_status(c);
 }
 
 // ---- BIH replication ----------------------------------------------------------------------------
@@ -800,6 +876,14 @@ int bihrt_bih_copy(bihrt_ctx* dst, bihrt_ctx* src) {
     BIHRT_CUDA(dst, cudaStreamWaitEvent(dst->stream, ev, 0));
     BIHRT_CUDA(dst, cudaMemcpyPeerAsync(dst->d_blob, dst->device, src->d_blob, src->device, (size_t)bytes, dst->stream));
     cudaEventDestroy(ev);                                        // released once the recorded work has completed
+    // ... and the source's next build must not overwrite the blob while the copy is still reading it
+    cudaEvent_t done = nullptr;
+    BIHRT_CUDA(dst, cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+    BIHRT_CUDA(dst, cudaEventRecord(done, dst->stream));
+    BIHRT_CUDA(dst, cudaSetDevice(src->device));
+    BIHRT_CUDA(dst, cudaStreamWaitEvent(src->stream, done, 0));
+    BIHRT_CUDA(dst, cudaSetDevice(dst->device));
+    cudaEventDestroy(done);
     return bihrt_bih_adopt(dst, src->n);
 }
 

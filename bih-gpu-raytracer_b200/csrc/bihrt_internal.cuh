@@ -91,13 +91,26 @@ struct bihrt_ctx {
 
     // trace
     uint32_t* d_fb = nullptr; int fb_w = 0, fb_h = 0; size_t fb_cap = 0;
+    bool      fb_exported = false;                     // a CUDA IPC handle of d_fb is out: the allocation must not move
+    uint32_t* h_status = nullptr;                      // pinned + mapped host word: hdr->status of the last build (written by k_nodes)
+    uint32_t* d_status_map = nullptr;                  // its device alias
     void*     d_io = nullptr; size_t io_cap = 0;      // staging for host ray lists / results
     unsigned long long* d_counters = nullptr;
     uint32_t* d_work = nullptr;                        // persistent-kernel work counter
     // cost-ordered tiles: the longest unit of every 32x32-pixel tile measured by the previous launch of the same frame
     // geometry, and the tile order (most expensive first) derived from it
     // (a few slots keyed by the launch geometry, so that a frame's camera pass and its shadow / bounce lists each keep theirs)
-    struct TileSlot { uint64_t sig = 0; bool valid = false; uint32_t *cost = nullptr, *order = nullptr; size_t cap = 0; };
+    // (a slot is reused only for a launch whose geometry matches FIELD BY FIELD: a permutation of the wrong size would skip tiles)
+    struct TileKey {
+        int mode = -1, w = 0, h = 0, gshift = 0, nsamp = 0, shard_index = 0, shard_count = 0, il_index = 0, il_count = 0, il_cshift = 0;
+        int64_t nrays = 0; uint32_t ntiles = 0;
+        bool operator==(const TileKey& o) const {
+            return mode == o.mode && w == o.w && h == o.h && gshift == o.gshift && nsamp == o.nsamp && shard_index == o.shard_index &&
+                   shard_count == o.shard_count && il_index == o.il_index && il_count == o.il_count && il_cshift == o.il_cshift &&
+                   nrays == o.nrays && ntiles == o.ntiles;
+        }
+    };
+    struct TileSlot { TileKey key; bool valid = false; uint32_t *cost = nullptr, *order = nullptr; size_t cap = 0; };
     TileSlot tile_slots[4]; int tile_next = 0;
 
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -117,6 +130,7 @@ struct bihrt_ctx {
     int64_t kernel_launches = 0;
     int opt_build_graph = 1;            // replay the build as a captured CUDA graph
     cudaGraphExec_t build_graph_exec = nullptr; int64_t build_graph_n = -1, build_graph_launches = 0;
+    int opt_debug_trip_watchdog = 0;   // tests: the next build reports this watchdog status (as if a sort pass had timed out)
     int opt_profile = 0;    // record an event after every build stage (bihrt_get_stat "build_stage_us_<i>")
     cudaEvent_t prof_ev[BIHRT_PROF_EVENTS] = {};
     int prof_count = 0;

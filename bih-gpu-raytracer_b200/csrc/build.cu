@@ -92,12 +92,12 @@ __device__ __forceinline__ void minmax3(float a, float b, float c, float& mn, fl
 
 // ------------------------------------------------------------------------------------------
 // also clears the look-back words of the four sort passes (one launch instead of a kernel + a memset node)
-__global__ void __launch_bounds__(256) k_init(uint32_t* hist, uint32_t* enc, BihHeader* hdr, uint32_t n, uint4* __restrict__ lookback, uint32_t lb_vec4) {
+__global__ void __launch_bounds__(256) k_init(uint32_t* hist, uint32_t* enc, BihHeader* hdr, uint32_t n, uint4* __restrict__ lookback, uint32_t lb_vec4, uint32_t status0) {
     for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < lb_vec4; i += gridDim.x * 256u) lookback[i] = make_uint4(0u, 0u, 0u, 0u);
     if (blockIdx.x != 0) return;
     for (int i = threadIdx.x; i < H_WORDS; i += blockDim.x) hist[i] = 0;
     if (threadIdx.x < 3) { enc[threadIdx.x] = 0xFFFFFFFFu; enc[3 + threadIdx.x] = 0u; }
-    if (threadIdx.x == 0) { hdr->n = n; hdr->nu = 0; hdr->status = 0; hdr->root_axis = 0; }
+    if (threadIdx.x == 0) { hdr->n = n; hdr->nu = 0; hdr->status = status0; hdr->root_axis = 0; }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -553,9 +553,10 @@ __device__ __forceinline__ float heap_range(const float* __restrict__ h, uint32_
 
 __global__ void __launch_bounds__(128) k_nodes(const uint32_t* __restrict__ umc, const uint32_t* __restrict__ first,
                                                BihHeader* hdr, const float* __restrict__ heaps, uint32_t P,
-                                               BihNode* __restrict__ nodes) {
+                                               BihNode* __restrict__ nodes, uint32_t* __restrict__ status_map) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int nu = (int)hdr->nu;
+    if (idx == 0) *status_map = hdr->status;      // last kernel of the build: the watchdog word, mirrored into mapped host memory
     if (idx > nu - 2) return;
     const uint32_t cur = __ldg(umc + idx);
     // common-prefix length with leaf j, -1 outside the array (R/src/CUDAKernels.cu:600-614,628-631)
@@ -618,7 +619,7 @@ int bihrt_build_launch(bihrt_ctx* c) {
     PROF_MARK();
     const uint32_t lb_vec4 = (uint32_t)((lb_words + 3) / 4);        // the buffer is allocated with 16 spare words
     k_init<<<(int)max(1u, min((uint32_t)c->sm_count, (lb_vec4 + 1023u) / 1024u)), 256, 0, st>>>(c->d_hist, c->d_scenebox_enc, c->d_hdr, n,
-                                                                                      reinterpret_cast<uint4*>(c->d_lookback), lb_vec4);
+                                                                                      reinterpret_cast<uint4*>(c->d_lookback), lb_vec4, (uint32_t)c->opt_debug_trip_watchdog);
     PROF_MARK();   // 1: after init + memsets
     const int stream_grid = (int)max(1u, min((uint32_t)(c->sm_count * 3), ((n >> 2) + 255) / 256));
     k_scene_box<<<stream_grid, 256, 0, st>>>(c->d_tri_in, n, c->d_scenebox_enc);
@@ -651,7 +652,7 @@ int bihrt_build_launch(bihrt_ctx* c) {
         launches++;
     }
     PROF_MARK();   // 10: after upper heap levels
-    k_nodes<<<(n + 127) / 128, 128, 0, st>>>(c->d_umc, c->d_first, c->d_hdr, c->d_heaps, P, c->d_nodes);
+    k_nodes<<<(n + 127) / 128, 128, 0, st>>>(c->d_umc, c->d_first, c->d_hdr, c->d_heaps, P, c->d_nodes, c->d_status_map);
     PROF_MARK();   // 11: after nodes
     PROF_MARK();   // 12: after reorder
     c->prof_count = pe;
@@ -689,7 +690,7 @@ int bihrt_refit_launch(bihrt_ctx* c) {
         k_heap_up<<<(used + 255) / 256, 256, 0, st>>>(c->d_heaps, P, lvl, used);
         launches++;
     }
-    k_nodes<<<(n + 127) / 128, 128, 0, st>>>(c->d_umc, c->d_first, c->d_hdr, c->d_heaps, P, c->d_nodes);
+    k_nodes<<<(n + 127) / 128, 128, 0, st>>>(c->d_umc, c->d_first, c->d_hdr, c->d_heaps, P, c->d_nodes, c->d_status_map);
     c->kernel_launches += 5 + launches;
     BIHRT_CUDA(c, cudaGetLastError());
     return BIHRT_OK;

@@ -56,11 +56,11 @@ __device__ __forceinline__ uint32_t pack_colour(uint32_t hits, int samples) {
 
 template <bool COUNTED>
 __device__ __forceinline__ void test_leaf(const char* __restrict__ first_tri, float ox, float oy, float oz,
-                                          float dx, float dy, float dz, Hit& h, uint32_t& ntris) {
+                                          float dx, float dy, float dz, Hit& h, uint32_t& ntris, uint32_t& wleaf) {
     const float4* p = reinterpret_cast<const float4*>(first_tri);
     for (;;) {
         const float4 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2);
-        if (COUNTED) ntris++;
+        if (COUNTED) { ntris++; const uint32_t am = __activemask(); wleaf += ((threadIdx.x & 31) == __ffs(am) - 1); }
         const float e1x = q0.w, e1y = q1.x, e1z = q1.y, e2x = q1.z, e2y = q1.w, e2z = q2.x;
         // pvec = cross(dir, e2); det = dot(e1, pvec)                       R/src/CUDAKernels.cu:24-26
         const float px = __fsub_rn(__fmul_rn(dy, e2z), __fmul_rn(e2y, dz));
@@ -105,8 +105,10 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
     const char* __restrict__ tris_b = reinterpret_cast<const char*>(a.tris);
     const BihTri* __restrict__ tris = a.tris;
     const uint32_t nu = a.hdr->nu;
+    if (a.hdr->status != 0) return;             // the build's device watchdog tripped: trace nothing rather than garbage (the host reports it)
     const float blo[3] = { a.hdr->lo[0], a.hdr->lo[1], a.hdr->lo[2] }, bhi[3] = { a.hdr->hi[0], a.hdr->hi[1], a.hdr->hi[2] };
     uint32_t nnodes = 0, ntris = 0, maxsp = 0;
+    uint32_t wnode = 0, wleaf = 0;              // COUNTED: warp-level executions of the node step / the triangle test (SIMD efficiency = lane steps / 32 / these)
 
     // work items
     uint64_t total;
@@ -163,7 +165,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
         if (idle && (busy == 0 || (thresh < 32 && __popc(__ballot_sync(FULL, cur == NONE && (tracing || item != ~0ull || MODE == 0))) >= thresh))) {
             const bool fresh = (busy == 0);          // the warp starts a new packet together
             int new_thresh = -1;
-            bool want_item = false;
+            bool want_item = false, finishing = false;
             if (cur == NONE) {
                 if (tracing) {                                   // record the ray that just ended
                     tracing = false;
@@ -176,25 +178,30 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
                     }
                     s++;
                     if (s == nsamp) {
-                        if (MODE == 1 && gshift > 0) {
-                            // the lanes of one pixel finish together (always, when the warp moves in lock step)
-                            const uint32_t am = __activemask();
-                            const uint32_t same = __match_any_sync(am, pixel);
-                            const uint32_t sum = __reduce_add_sync(same, hits);
-                            if (lane == __ffs(same) - 1) {
-                                // colours: the pixel's lanes hold all its samples -> one plain store of the final value
-                                // (a.fb may be another GPU's framebuffer: the store then travels over NVLink);
-                                // counts (a pixel's samples are spread over ranks): one atomic per pixel and warp
-                                if (direct) a.fb[pixel] = pack_colour(sum, nsamp << gshift);
-                                else if (sum) atomicAdd(&a.fb[pixel], sum);
-                            }
-                        }
+                        if (MODE == 1 && gshift > 0) finishing = true;      // written below, by the pixel's lanes together
                         else if (MODE == 1 && (a.flags & BIHRT_RENDER_COUNTS)) a.fb[pixel] = hits;     // resolved after the reduce
                         else if (MODE == 1) a.fb[pixel] = pack_colour(hits, nsamp);
                         item = ~0ull;
                     }
                 }
                 want_item = (item == ~0ull);
+            }
+            if (MODE == 1 && gshift > 0) {
+                // the lanes of one pixel finish together (always, when the warp moves in lock step).  The participants are
+                // named by a ballot taken where the whole warp is converged (the refill block is entered warp-uniformly),
+                // not by __activemask() inside the divergent branch, which promises nothing about convergence.
+                const uint32_t fin = __ballot_sync(FULL, finishing);
+                if (finishing) {
+                    const uint32_t same = __match_any_sync(fin, pixel);
+                    const uint32_t sum = __reduce_add_sync(same, hits);
+                    if (lane == __ffs(same) - 1) {
+                        // colours: the pixel's lanes hold all its samples -> one plain store of the final value
+                        // (a.fb may be another GPU's framebuffer: the store then travels over NVLink);
+                        // counts (a pixel's samples are spread over ranks): one atomic per pixel and warp
+                        if (direct) a.fb[pixel] = pack_colour(sum, nsamp << gshift);
+                        else if (sum) atomicAdd(&a.fb[pixel], sum);
+                    }
+                }
             }
             // the packet that just drained: its duration is the cost of its tile for the next frame's order
             if (MODE != 0 && fresh && a.tile_cost && unit_tile != 0xFFFFFFFFu) {
@@ -379,7 +386,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
                 const float4* np;
                 asm("mad.wide.u32 %0, %1, 16, %2;" : "=l"(np) : "r"(cur >> 2), "l"(nodes_b));
                 const float4 nd = __ldg(np);
-                if (COUNTED) nnodes++;
+                if (COUNTED) { nnodes++; const uint32_t am = __activemask(); wnode += (lane == __ffs(am) - 1); }
                 const uint32_t rl = __float_as_uint(nd.z), rr = __float_as_uint(nd.w);
                 const bool neg = oi.y < 0.f;                           // near = sign[axis], :286
                 const float t0 = __fmul_rn(__fsub_rn(nd.x, oi.x), oi.y);   // :288-289
@@ -400,7 +407,13 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
                         cur = refn; pMax = nMax;
                     }
                     sp++;
-                    if (COUNTED) maxsp = max(maxsp, (uint32_t)sp);
+                    // depth: a root-to-leaf path pushes at most one item per Morton bit, so sp <= 30 < STACK_DEPTH by
+                    // construction; the instrumented build reports the deepest stack (counters[2]) and refuses to run past
+                    // the array, -DBIHRT_DEBUG_STACK traps in every build
+                    if (COUNTED) { maxsp = max(maxsp, (uint32_t)sp); if (sp >= STACK_DEPTH) { maxsp = 0x7fffffffu; sp = STACK_DEPTH - 1; } }
+#ifdef BIHRT_DEBUG_STACK
+                    if (sp >= STACK_DEPTH) __trap();
+#endif
                 } else if (go_near) { cur = refn; pMax = nMax; }
                 else if (go_far) { cur = reff; rMin = tf; pMin = fMin; }
                 else POP_VALID();
@@ -416,7 +429,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
         if (cur + 1u > 0x80000000u) {
             const char* tp;
             asm("mad.wide.u32 %0, %1, 12, %2;" : "=l"(tp) : "r"(cur & 0x7FFFFFFCu), "l"(tris_b));
-            test_leaf<COUNTED>(tp, ox, oy, oz, dx, dy, dz, h, ntris);
+            test_leaf<COUNTED>(tp, ox, oy, oz, dx, dy, dz, h, ntris, wleaf);
             if (MODE == 0 && a.any_hit && h.slot >= 0) { sp = 0; cur = NONE; }      // occluded: nothing else to learn
             else POP_VALID();
         }
@@ -436,6 +449,8 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
             atomicAdd(&a.counters[1], (unsigned long long)ntris);
             atomicMax(&a.counters[2], (unsigned long long)maxsp);
         }
+        wnode = __reduce_add_sync(FULL, wnode); wleaf = __reduce_add_sync(FULL, wleaf);
+        if (lane == 0) { atomicAdd(&a.counters[4], (unsigned long long)wnode); atomicAdd(&a.counters[5], (unsigned long long)wleaf); }
     }
 }
 
@@ -569,7 +584,14 @@ int bihrt_trace_launch(bihrt_ctx* c, const TraceArgs& a_in, int mode, bool count
     // cost-ordered tiles (camera modes, one global counter): reuse the order measured by the previous launch of the same
     // frame geometry; always record the costs of this one
     uint32_t ntiles = 0;
-    uint64_t sig = 0;
+    bihrt_ctx::TileKey key;
+    // the 32-bit work counters (global and per-SM) must not wrap: padded items of this launch
+    if (mode != 0) {
+        const int tx = (a.w + 31) / 32, ty = (a.h + 31) / 32, T = tx * ty;
+        const int mine = T > a.shard_index ? (T - a.shard_index + a.shard_count - 1) / a.shard_count : 0;
+        if ((((uint64_t)mine * 1024u) << a.gshift) >= (1ull << 32) - (1ull << 24))
+            return bihrt_fail(c, BIHRT_ERR_INVALID, "launch of %d tiles x 1024 pixels x %d lane groups exceeds the 32-bit work counter", mine, 1 << a.gshift);
+    }
     // (launches of tens of milliseconds have no tail to speak of and lose ~0.5 % to the changed tile neighbourhood; tiny
     // scenes have no long units -- the Cornell box frame is 25 us -- and only pay for the extra k_tile_order launch)
     const bool order_on = a.queues == 1 && (c->opt_tile_order > 1 || (c->opt_tile_order == 1 && rays >= (64ll << 10) && rays < (48ll << 20) && c->n >= 10000));
@@ -577,22 +599,23 @@ int bihrt_trace_launch(bihrt_ctx* c, const TraceArgs& a_in, int mode, bool count
         if (mode == 0) {
             // ray lists: chunks of 1024 rays play the role of tiles; the order is reused for lists of the same length (the
             // next frame's shadow / bounce batch), stale costs only change the schedule, never a result
-            if (a.nrays > 1024 && a.nrays <= (65536ll << 10)) { ntiles = (uint32_t)((a.nrays + 1023) >> 10); sig = (1ull << 63) | (uint64_t)a.nrays; }
+            if (a.nrays > 1024 && a.nrays <= (65536ll << 10)) { ntiles = (uint32_t)((a.nrays + 1023) >> 10); key.nrays = a.nrays; }
         } else {
             const int tx = (a.w + 31) / 32, ty = (a.h + 31) / 32, T = tx * ty;
             const int mine = T > a.shard_index ? (T - a.shard_index + a.shard_count - 1) / a.shard_count : 0;
             if (mine > 1 && mine <= 65536) ntiles = (uint32_t)mine;
-            sig = ((uint64_t)a.w << 48) ^ ((uint64_t)a.h << 32) ^ ((uint64_t)a.gshift << 28) ^ ((uint64_t)a.shard_index << 20) ^
-                  ((uint64_t)a.shard_count << 12) ^ ((uint64_t)a.il_index << 6) ^ (uint64_t)a.il_count ^ ((uint64_t)((a.s_end - a.s_begin) & 0x7f) << 56);
+            key.w = a.w; key.h = a.h; key.gshift = a.gshift; key.nsamp = a.s_end - a.s_begin; key.shard_index = a.shard_index;
+            key.shard_count = a.shard_count; key.il_index = a.il_index; key.il_count = a.il_count; key.il_cshift = a.il_cshift;
         }
+        key.mode = mode == 0 ? 0 : 1; key.ntiles = ntiles;
     }
     bihrt_ctx::TileSlot* slot = nullptr;
     if (ntiles) {
-        for (auto& ts : c->tile_slots) if (ts.cap && ts.sig == sig) slot = &ts;
+        for (auto& ts : c->tile_slots) if (ts.cap && ts.key == key) slot = &ts;
         if (!slot) {                                  // take the next slot round-robin
             slot = &c->tile_slots[c->tile_next];
             c->tile_next = (c->tile_next + 1) % 4;
-            slot->sig = sig; slot->valid = false;
+            slot->key = key; slot->valid = false;
         }
         if ((size_t)ntiles > slot->cap) {
             if (slot->cost) cudaFree(slot->cost);

@@ -106,7 +106,15 @@ BIHRT_API int         bihrt_version(void);
 BIHRT_API int         bihrt_create(bihrt_ctx** out, const bihrt_config* cfg);   /* replaces Renderer::Init + GPUArrayManager ctor, R/src/Renderer.cpp:87-105 */
 BIHRT_API void        bihrt_destroy(bihrt_ctx* ctx);
 BIHRT_API const char* bihrt_last_error(const bihrt_ctx* ctx);                   /* replaces checkCudaErrors' stderr print */
-BIHRT_API int         bihrt_set_stream(bihrt_ctx* ctx, void* cuda_stream);      /* run on a caller-owned stream (NULL = own stream) */
+/* Stream of the context.  A new context runs on its OWN private non-blocking stream.  bihrt_set_stream takes a
+ * cudaStream_t with CUDA's own meaning -- NULL (0) is the legacy default stream, exactly what
+ * torch.cuda.current_stream().cuda_stream is while torch runs on its default stream -- or BIHRT_STREAM_OWN to go back
+ * to the private stream.  Work of a caller that runs on ANOTHER stream is not ordered with the library's: either hand
+ * that stream to bihrt_set_stream, or order the two with events on the handle bihrt_get_stream returns (the Python
+ * mirror does this for torch tensors). */
+#define BIHRT_STREAM_OWN ((void*)(intptr_t)-1)
+BIHRT_API int         bihrt_set_stream(bihrt_ctx* ctx, void* cuda_stream);
+BIHRT_API int         bihrt_get_stream(bihrt_ctx* ctx, void** cuda_stream);     /* the cudaStream_t the context launches on */
 BIHRT_API int         bihrt_sync(bihrt_ctx* ctx);                               /* replaces the cudaDeviceSynchronize after each step, R/src/Renderer.cpp:428-503 */
 BIHRT_API int         bihrt_set_option(bihrt_ctx* ctx, const char* name, int64_t value);  /* tuning knobs, see DESIGN.md */
 BIHRT_API int         bihrt_get_stat(bihrt_ctx* ctx, const char* name, int64_t* value);   /* "kernel_launches": kernels of this library launched so far */
@@ -187,6 +195,10 @@ BIHRT_API int bihrt_render_interleaved_to(bihrt_ctx* ctx, const bihrt_camera* ca
 BIHRT_API int bihrt_framebuffer_ipc_export(bihrt_ctx* ctx, int32_t w, int32_t h, void* handle64);
 BIHRT_API int bihrt_framebuffer_ipc_open(bihrt_ctx* ctx, const void* handle64, uint32_t** peer_fb);
 BIHRT_API int bihrt_framebuffer_ipc_close(bihrt_ctx* ctx, uint32_t* peer_fb);
+/* While a handle is out the exporting context refuses (BIHRT_ERR_STATE) to reallocate its framebuffer for a larger
+ * frame -- the peers would keep storing into freed memory.  Call this once every peer has closed its mapping.  (The
+ * same care is the caller's for a raw bihrt_framebuffer() pointer handed to another context as target_fb.) */
+BIHRT_API int bihrt_framebuffer_ipc_unexport(bihrt_ctx* ctx);
 /* Per-sample hit buffers of the same rays bihrt_render traces (index = (j*w+i)*spp + s); device or
  * host outputs, any may be NULL.  Used by the parity tests. */
 BIHRT_API int bihrt_render_hits(bihrt_ctx* ctx, const bihrt_camera* cam, int32_t w, int32_t h, int32_t spp,

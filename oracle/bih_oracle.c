@@ -588,6 +588,26 @@ ORC_API void orc_camera_rays(const float* cam12, int w, int h, int spp, int jitt
             }
 }
 
+/* The same rays for a window [x0, x0+ww) x [y0, y0+wh) of the w x h frame (pixel ids and u,v are the FRAME's), in
+ * window-row-major order: lets a test check a few tiles of a frame too large to trace on the CPU. */
+ORC_API void orc_camera_rays_window(const float* cam12, int w, int h, int spp, int jitter, uint64_t seed,
+                                    int x0, int y0, int ww, int wh, float* rays6) {
+    for (int j = 0; j < wh; j++)
+        for (int i = 0; i < ww; i++)
+            for (int s = 0; s < spp; s++) {
+                uint32_t pixel = (uint32_t)((y0 + j) * w + (x0 + i));
+                float ru = jitter ? jitter01(seed, pixel, (uint32_t)s, 0) : 0.5f;
+                float rv = jitter ? jitter01(seed, pixel, (uint32_t)s, 1) : 0.5f;
+                float u = ((float)(x0 + i) + ru) / (float)w;
+                float v = ((float)(y0 + j) + rv) / (float)h;
+                float* r = rays6 + 6 * (((int64_t)j * ww + i) * spp + s);
+                for (int k = 0; k < 3; k++) {
+                    r[k] = cam12[k];
+                    r[3 + k] = cam12[3 + k] + u * cam12[6 + k] + v * cam12[9 + k] - cam12[k];
+                }
+            }
+}
+
 /* cudaRender accumulate + rgbToInt, R/src/CUDAKernels.cu:82-88,385-387,412-422:
  * hit -> (255,255,0), miss -> (20,20,40), mean over spp, pack r | g<<8 | b<<16.
  * hit_slot has w*h*spp entries in the order produced by orc_camera_rays. */

@@ -101,6 +101,15 @@ def camera_rays(cam12, w, h, spp=1, jitter=False, seed=1984):
     return rays
 
 
+def camera_rays_window(cam12, w, h, x0, y0, ww, wh, spp=1, jitter=False, seed=1984):
+    """Rays of the pixels [x0, x0+ww) x [y0, y0+wh) of the w x h frame (frame pixel ids / u,v), window-row-major."""
+    cam12 = np.ascontiguousarray(cam12, dtype=np.float32).reshape(12)
+    rays = np.empty((wh * ww * spp, 6), np.float32)
+    lib().orc_camera_rays_window(_p(cam12), C.c_int(w), C.c_int(h), C.c_int(spp), C.c_int(int(jitter)), C.c_uint64(seed),
+                                 C.c_int(x0), C.c_int(y0), C.c_int(ww), C.c_int(wh), _p(rays))
+    return rays
+
+
 def pack_framebuffer(hit_slot, w, h, spp):
     hit_slot = np.ascontiguousarray(hit_slot, dtype=np.int32)
     fb = np.empty(w * h, np.uint32)

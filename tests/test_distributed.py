@@ -50,6 +50,13 @@ class FakeRenderer:
     def sync(self):
         pass
 
+    # stream ordering with torch's current stream (events in the real Renderer): record the calls
+    def wait_torch(self):
+        self.__dict__.setdefault("order_log", []).append("ctx_waits_torch")
+
+    def torch_wait(self):
+        self.__dict__.setdefault("order_log", []).append("torch_waits_ctx")
+
     # in-place replication: the blob region of an n-triangle scene is the broadcast buffer itself
     def bih_region_tensor(self, n):
         import torch
@@ -90,6 +97,8 @@ def _worker(rank, world, port, q):
         nb = multi.replicate_bih_inplace(r, dist, 37, src=0)
         ok_blob = ok_blob and nb == 64 + 64 * 37 and np.array_equal(r.region.numpy(), (np.arange(nb) % 251).astype(np.uint8)) \
             and (rank == 0 or getattr(r, "adopted", None) == 37) and (rank != 0 or not hasattr(r, "adopted"))
+        # the in-place broadcast is bracketed by the two stream orderings (torch waits for the build, the context waits for the collective)
+        ok_blob = ok_blob and r.order_log[-2:] == ["torch_waits_ctx", "ctx_waits_torch"]
         tok = torch.ones(1, dtype=torch.int32)
         multi.frame_barrier(dist, tok)
         ok_blob = ok_blob and int(tok.item()) == world
