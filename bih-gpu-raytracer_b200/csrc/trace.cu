@@ -38,6 +38,19 @@
 #define TRACE_MIN_BLOCKS 8        // <= 64 registers per thread
 #endif
 
+// The newest TRACE_SSTACK items of every lane's stack live in SHARED memory (slot i & (TRACE_SSTACK-1) of a per-thread column:
+// 16-byte accesses of consecutive threads are conflict-free whatever row each lane is on); older items spill to the
+// local-memory array, which a root-to-leaf path of a shallow tree never reaches.  Local memory is cached in L1 like the nodes
+// and triangles that stream through it, so a popped item is often an L2 round trip away (the pop was the top stall of the
+// 1 spp profile next to the node fetch itself); shared memory is never evicted.  0 = everything in local memory.
+// MEASURED (round 2, B200, 1 M triangles; Mrays/s with 0 / 4 / 8 shared items): 1080p x 1 spp 2887 / 2661 / 2901, x 4 spp
+// 3805 / 3506 / 3634, x 16 spp 5015 / 4594 / 4694, 4K x 16 spp 5983 / 5446 / 5519; 10 M triangles and the atrium lose 2-7 %
+// too.  The ring bookkeeping costs more issue slots than the pops save, and 16 KB x items of shared memory per SM come out
+// of the L1 the nodes live in.  Shipped: 0.
+#ifndef TRACE_SSTACK
+#define TRACE_SSTACK 0
+#endif
+
 // (double)det < 0.000001 (R/src/CUDAKernels.cu:28)  <=>  det < 0x358637be as binary32
 #define DET_EPS __uint_as_float(0x358637beu)
 
@@ -143,6 +156,28 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
     bool tracing = false;                      // a ray is in flight (its result has not been recorded)
     uint4 stack[STACK_DEPTH];
     int sp = 0;
+#if TRACE_SSTACK > 0
+    __shared__ uint4 s_stack[TRACE_SSTACK * TRACE_THREADS];
+    uint4* const my_stack = s_stack + threadIdx.x;
+    int lo = 0;                                // items [0, lo) are in local memory, [lo, sp) in shared memory; sp - lo <= TRACE_SSTACK
+#define STACK_RESET() do { sp = 0; lo = 0; } while (0)
+#define STACK_PUSH(item)                                                                                    \
+        do {                                                                                                \
+            if (sp - lo == TRACE_SSTACK) { stack[lo] = my_stack[(lo & (TRACE_SSTACK - 1)) * TRACE_THREADS]; lo++; }   \
+            my_stack[(sp & (TRACE_SSTACK - 1)) * TRACE_THREADS] = (item);                                   \
+            sp++;                                                                                           \
+        } while (0)
+#define STACK_POP(e)                                                                                        \
+        do {                                                                                                \
+            sp--;                                                                                           \
+            (e) = my_stack[(sp & (TRACE_SSTACK - 1)) * TRACE_THREADS];                                      \
+            if (sp == lo && lo > 0) { lo--; my_stack[(lo & (TRACE_SSTACK - 1)) * TRACE_THREADS] = stack[lo]; }  \
+        } while (0)
+#else
+#define STACK_RESET() do { sp = 0; } while (0)
+#define STACK_PUSH(item) do { stack[sp] = (item); sp++; } while (0)
+#define STACK_POP(e) do { sp--; (e) = stack[sp]; } while (0)
+#endif
     const uint32_t root_ref = BIH_REF_NODE(0, a.hdr->root_axis);
     const bool vote = WALK > 0 || a.vote_wait != 0;
     int thresh = a.refill_threshold;          // lanes that must be idle before a partial refill (warp-uniform)
@@ -323,7 +358,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
                 }
                 my_ray[0] = make_float2(ox, ix); my_ray[1] = make_float2(oy, iy); my_ray[2] = make_float2(oz, iz);
                 // occlusion queries (MODE 0, any_hit): only hits before tmax count, and the first one found ends the ray
-                h.t = (MODE == 0 && a.any_hit) ? a.tmax : FLT_MAX; h.slot = -1; sp = 0; tracing = true;
+                h.t = (MODE == 0 && a.any_hit) ? a.tmax : FLT_MAX; h.slot = -1; STACK_RESET(); tracing = true;
                 // slab test against the scene box, R/src/CUDAKernels.cu:237-262 (same operation order)
                 bool in = nu > 0;
                 float tMin = __fmul_rn(__fsub_rn(ix < 0.f ? bhi[0] : blo[0], ox), ix);
@@ -368,8 +403,8 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
         do {                                                                                                \
             cur = NONE;                                                                                     \
             while (sp > 0) {                                                                                \
-                sp--;                                                                                       \
-                const uint4 e = stack[sp];                                                                  \
+                uint4 e;                                                                                    \
+                STACK_POP(e);                                                                               \
                 const float m = fminf(__uint_as_float(e.w), h.t);                                           \
                 if (__uint_as_float(e.z) <= m) { cur = e.x; rMin = __uint_as_float(e.y); pMin = __uint_as_float(e.z); pMax = m; break; } \
             }                                                                                               \
@@ -400,13 +435,12 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
                 if (go_near && go_far) {
                     // near before far, except a far LEAF next to a near NODE is tested first (:344-349)
                     if ((int)refn >= 0 && (int)reff < 0) {
-                        stack[sp] = make_uint4(refn, __float_as_uint(rMin), __float_as_uint(pMin), __float_as_uint(nMax));
+                        STACK_PUSH(make_uint4(refn, __float_as_uint(rMin), __float_as_uint(pMin), __float_as_uint(nMax)));
                         cur = reff; rMin = tf; pMin = fMin;
                     } else {
-                        stack[sp] = make_uint4(reff, __float_as_uint(tf), __float_as_uint(fMin), __float_as_uint(pMax));
+                        STACK_PUSH(make_uint4(reff, __float_as_uint(tf), __float_as_uint(fMin), __float_as_uint(pMax)));
                         cur = refn; pMax = nMax;
                     }
-                    sp++;
                     // depth: a root-to-leaf path pushes at most one item per Morton bit, so sp <= 30 < STACK_DEPTH by
                     // construction; the instrumented build reports the deepest stack (counters[2]) and refuses to run past
                     // the array, -DBIHRT_DEBUG_STACK traps in every build
@@ -430,10 +464,13 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
             const char* tp;
             asm("mad.wide.u32 %0, %1, 12, %2;" : "=l"(tp) : "r"(cur & 0x7FFFFFFCu), "l"(tris_b));
             test_leaf<COUNTED>(tp, ox, oy, oz, dx, dy, dz, h, ntris, wleaf);
-            if (MODE == 0 && a.any_hit && h.slot >= 0) { sp = 0; cur = NONE; }      // occluded: nothing else to learn
+            if (MODE == 0 && a.any_hit && h.slot >= 0) { STACK_RESET(); cur = NONE; }      // occluded: nothing else to learn
             else POP_VALID();
         }
 #undef POP_VALID
+#undef STACK_RESET
+#undef STACK_PUSH
+#undef STACK_POP
         __syncwarp();
     }
 
