@@ -765,6 +765,22 @@ def run_ours(args, rank, world, local_rank):
                     e["animated_frame_1080p_1spp"] = {"build_ms": bms, "trace_ms": tms, "frame_ms": fms, "fps": 1e3 / fms,
                                                       "refit_ms_nonparity": rms}
                     e["moving_camera_1080p_1spp"] = moving_camera(r, scenes, timed_loop, 1920, 1080)
+                if key in ("1m", "10m"):
+                    # quality mode (NOT a parity path, reported separately): 63-bit Morton keys, leaves capped at 4
+                    try:
+                        r.set_option("morton_bits", 63); r.set_option("leaf_cap", 4)
+                        qb = med(lambda: r.build())
+                        cq = r.render_counted(c2, 1920, 1080, spp=1)
+                        e["quality_mode_63bit_cap4"] = {
+                            "parity": False, "leaves": r.build_info()["nu"], "build_ms_per_mtri": qb / (len(t2) / 1e6),
+                            "primary_mrays_s_1080p_1spp": primary(c2, 1920, 1080, 1), "primary_mrays_s_1080p_4spp": primary(c2, 1920, 1080, 4),
+                            "nodes_per_ray": cq["nodes"] / cq["rays"], "tris_per_ray": cq["tris"] / cq["rays"],
+                            "what": "non-parity tree: 21-bit grid per axis, ties broken by position, subtrees of <= 4 triangles collapsed into leaves; hits == brute force "
+                                    "(tests/test_gpu_quality.py)"}
+                    except Exception as ex:       # noqa
+                        e["quality_mode_63bit_cap4"] = {"error": repr(ex)[:200]}
+                    r.set_option("morton_bits", 30)
+                    r.build()
                 if key == "10m":     # config 4: 4K x 16 spp
                     c4 = scenes.pinhole_camera(aspect=3840 / 2160)
                     e["primary_mrays_s_4k_16spp"] = 3840 * 2160 * 16 / (med(lambda: r.render(c4, 3840, 2160, spp=16, jitter=True), 3) * 1e-3) / 1e6

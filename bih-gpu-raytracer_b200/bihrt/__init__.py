@@ -422,3 +422,6 @@ class Renderer:
 
     def bih_import(self, dev_buffer, nbytes):
         self._check(self._lib.bihrt_bih_import(self._ctx, _ptr(dev_buffer), C.c_uint64(nbytes)))
+
+
+from . import multi  # noqa: E402  (bihrt.multi: torch.distributed plumbing)

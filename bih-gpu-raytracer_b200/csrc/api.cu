@@ -69,6 +69,7 @@ static int ensure_capacity(bihrt_ctx* c, int64_t n, bool with_build_scratch) {
         dev_free(&c->d_tri_in);
         for (int i = 0; i < 2; i++) { dev_free(&c->d_keys[i]); dev_free(&c->d_vals[i]); }
         dev_free(&c->d_umc); dev_free(&c->d_first); dev_free(&c->d_lookback); dev_free(&c->d_heaps);
+        dev_free(&c->d_keys64[0]); dev_free(&c->d_keys64[1]); dev_free(&c->d_lookback_q); c->lookback_q_words = 0;
         c->cap_n = cap;
         c->have_scene = false; c->built = false;
         if (c->build_graph_exec) { cudaGraphExecDestroy(c->build_graph_exec); c->build_graph_exec = nullptr; }
@@ -113,7 +114,7 @@ int bihrt_create(bihrt_ctx** out, const bihrt_config* cfg) {
     c->stream = c->own_stream;
     cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1);
     int rc = 0;
-    rc |= dev_alloc(c, &c->d_hist, 2048);
+    rc |= dev_alloc(c, &c->d_hist, 4096);
     rc |= dev_alloc(c, &c->d_scenebox_enc, 8);
     rc |= dev_alloc(c, &c->d_counters, 8);
     rc |= dev_alloc(c, &c->d_work, 1024);
@@ -135,6 +136,7 @@ void bihrt_destroy(bihrt_ctx* c) {
     for (int i = 0; i < 2; i++) { dev_free(&c->d_keys[i]); dev_free(&c->d_vals[i]); }
     dev_free(&c->d_umc); dev_free(&c->d_first); dev_free(&c->d_hist); dev_free(&c->d_lookback);
     dev_free(&c->d_heaps); dev_free(&c->d_scenebox_enc);
+    dev_free(&c->d_keys64[0]); dev_free(&c->d_keys64[1]); dev_free(&c->d_lookback_q);
     dev_free(&c->d_fb); dev_free(&c->d_counters); dev_free(&c->d_work);
     for (auto& ts : c->tile_slots) { dev_free(&ts.cost); dev_free(&ts.order); }
     if (c->d_io) { cudaFree(c->d_io); c->d_io = nullptr; }
@@ -168,6 +170,8 @@ int bihrt_get_stream(bihrt_ctx* c, void** s) {
 // the device watchdog of the last build that has COMPLETED (never blocks)
 static int check_status(bihrt_ctx* c) {
     const uint32_t st = c->h_status ? *(volatile uint32_t*)c->h_status : 0u;
+    if (st & 0x100u) return bihrt_fail(c, BIHRT_ERR_STATE, "the BIH in this context is a %s tree but the context traces %s trees: set the option morton_bits "
+                                       "to the builder's value before adopting a replicated BIH", c->built_quality ? "parity" : "quality-mode", c->built_quality ? "quality-mode" : "parity");
     if (st) return bihrt_fail(c, BIHRT_ERR_INTERNAL, "device watchdog tripped during build (status %u): the BIH is invalid, rebuild", st);
     return BIHRT_OK;
 }
@@ -183,6 +187,18 @@ int bihrt_set_option(bihrt_ctx* c, const char* name, int64_t v) {
     if (!strcmp(name, "trace_blocks_per_sm")) c->opt_trace_blocks_per_sm = (int)v;
     else if (!strcmp(name, "trace_refill_threshold")) c->opt_refill_threshold = (int)std::max<int64_t>(1, std::min<int64_t>(32, v));
     else if (!strcmp(name, "build_graph")) c->opt_build_graph = (int)v;
+    else if (!strcmp(name, "morton_bits")) {
+        // 30: the reference's 10-bit grid (parity path).  63: quality mode (non-parity): 21 bits per axis, ties broken by position,
+        // subtrees of at most leaf_cap triangles collapsed into leaves.  Takes effect at the next bihrt_build / bihrt_bih_adopt.
+        if (v != 30 && v != 63) return bihrt_fail(c, BIHRT_ERR_INVALID, "morton_bits must be 30 (reference grid) or 63 (quality mode)");
+        c->opt_morton_bits = (int)v;
+        if (c->build_graph_exec) { cudaGraphExecDestroy(c->build_graph_exec); c->build_graph_exec = nullptr; }
+    }
+    else if (!strcmp(name, "leaf_cap")) {
+        if (v < 1 || v > 64) return bihrt_fail(c, BIHRT_ERR_INVALID, "leaf_cap must be 1..64");
+        c->opt_leaf_cap = (int)v;
+        if (c->build_graph_exec) { cudaGraphExecDestroy(c->build_graph_exec); c->build_graph_exec = nullptr; }
+    }
     else if (!strcmp(name, "debug_trip_watchdog")) {
         c->opt_debug_trip_watchdog = (int)v;
         if (c->build_graph_exec) { cudaGraphExecDestroy(c->build_graph_exec); c->build_graph_exec = nullptr; }    // the value is a kernel argument
@@ -308,9 +324,25 @@ int bihrt_scene_load_obj(bihrt_ctx* c, const char* path) {
 }
 
 // ---- build -------------------------------------------------------------------------------------
+// quality mode: 63-bit keys (two buffers) and the look-back words of 8 sort passes over 2048-key tiles, allocated on first use
+static int ensure_quality_scratch(bihrt_ctx* c) {
+    int rc;
+    const size_t cap = (size_t)c->cap_n;
+    for (int i = 0; i < 2; i++) if (!c->d_keys64[i] && (rc = dev_alloc(c, &c->d_keys64[i], cap + 8))) return rc;
+    const size_t need = 8 * ((cap + 2047) / 2048) * 256 + 16;
+    if (need > c->lookback_q_words) {
+        if ((rc = dev_alloc(c, &c->d_lookback_q, need))) { c->lookback_q_words = 0; return rc; }
+        c->lookback_q_words = need;
+    }
+    return BIHRT_OK;
+}
+
 int bihrt_build(bihrt_ctx* c) {
     ENTER(c);
     if (!c->have_scene || !c->d_tri_in) return bihrt_fail(c, BIHRT_ERR_STATE, "no scene loaded");
+    const bool quality = c->opt_morton_bits == 63;
+    if (quality) { int rq = ensure_quality_scratch(c); if (rq) return rq; }
+    auto build_launch = [&]() { return quality ? bihrt_build_launch_q(c) : bihrt_build_launch(c); };
     BIHRT_CUDA(c, cudaEventRecord(c->ev0, c->stream));
     if (c->n == 0) {
         BIHRT_CUDA(c, cudaMemsetAsync(c->d_hdr, 0, sizeof(BihHeader), c->stream));
@@ -324,7 +356,7 @@ int bihrt_build(bihrt_ctx* c) {
             cudaGraph_t g = nullptr;
             BIHRT_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
             const int64_t launches_before = c->kernel_launches;
-            int rc = bihrt_build_launch(c);
+            int rc = build_launch();
             cudaError_t e = cudaStreamEndCapture(c->stream, &g);
             if (rc) { if (g) cudaGraphDestroy(g); return rc; }
             if (e != cudaSuccess) return bihrt_fail(c, BIHRT_ERR_CUDA, "graph capture of the build failed: %s", cudaGetErrorString(e));
@@ -338,17 +370,18 @@ int bihrt_build(bihrt_ctx* c) {
         BIHRT_CUDA(c, cudaGraphLaunch(c->build_graph_exec, c->stream));
         c->kernel_launches += c->build_graph_launches;
     } else {
-        int rc = bihrt_build_launch(c);
+        int rc = build_launch();
         if (rc) return rc;
     }
     BIHRT_CUDA(c, cudaEventRecord(c->ev1, c->stream));
-    c->built = true; c->build_timed = true; c->topology_valid = c->n > 0;
+    c->built = true; c->build_timed = true; c->topology_valid = c->n > 0 && !quality; c->built_quality = quality && c->n > 0;
     return BIHRT_OK;
 }
 
 int bihrt_refit(bihrt_ctx* c) {
     ENTER(c);
     if (!c->have_scene || !c->d_tri_in) return bihrt_fail(c, BIHRT_ERR_STATE, "no scene loaded");
+    if (c->built_quality || c->opt_morton_bits == 63) return bihrt_fail(c, BIHRT_ERR_STATE, "bihrt_refit is not available in quality mode (morton_bits = 63)");
     if (!c->topology_valid) return bihrt_fail(c, BIHRT_ERR_STATE, "refit needs a full bihrt_build of the same triangle count first");
     BIHRT_CUDA(c, cudaEventRecord(c->ev0, c->stream));
     int rc = bihrt_refit_launch(c);
@@ -374,9 +407,9 @@ int bihrt_get_build_info(bihrt_ctx* c, bihrt_build_info* out) {
     if (rc) return rc;
     memset(out, 0, sizeof *out);
     out->n = h.n; out->nu = h.nu;
-    out->node_bytes = h.nu > 1 ? (int64_t)(h.nu - 1) * 16 : 0;
+    out->node_bytes = h.quality ? (h.n > 1 ? (int64_t)(h.n - 1) * 16 : 0) : (h.nu > 1 ? (int64_t)(h.nu - 1) * 16 : 0);
     out->tri_bytes = (int64_t)h.n * 48;
-    out->sort_passes = 4;
+    out->sort_passes = h.quality ? 8 : 4;
     if (c->build_timed) { float ms = 0; if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) out->last_build_ms = ms; else cudaGetLastError(); }
     return BIHRT_OK;
 }
@@ -385,6 +418,7 @@ int bihrt_export_reference_view(bihrt_ctx* c, bihrt_refview* v) {
     ENTER(c);
     if (!v) return BIHRT_ERR_INVALID;
     if (!c->built || !c->d_keys[0]) return bihrt_fail(c, BIHRT_ERR_STATE, "reference view needs a BIH built on this context");
+    if (c->built_quality) return bihrt_fail(c, BIHRT_ERR_STATE, "the reference view is defined for the reference's tree only (morton_bits = 30), not for a quality-mode build");
     BihHeader h;
     int rc = fetch_header(c, &h);
     if (rc) return rc;
@@ -788,7 +822,7 @@ int bihrt_bih_blob_bytes(bihrt_ctx* c, uint64_t* bytes) {
     BihHeader h;
     int rc = fetch_header(c, &h);
     if (rc) return rc;
-    *bytes = 64 + (uint64_t)(h.nu > 1 ? h.nu - 1 : 0) * 16 + (uint64_t)h.n * 48;
+    *bytes = 64 + (uint64_t)(h.quality ? (h.n > 1 ? h.n - 1 : 0) : (h.nu > 1 ? h.nu - 1 : 0)) * 16 + (uint64_t)h.n * 48;
     return BIHRT_OK;
 }
 
@@ -800,7 +834,7 @@ int bihrt_bih_export(bihrt_ctx* c, void* dev_dst, uint64_t bytes) {
     if (!dev_dst || bytes < need) return bihrt_fail(c, BIHRT_ERR_INVALID, "blob buffer too small (%llu < %llu)", (unsigned long long)bytes, (unsigned long long)need);
     BihHeader h;
     if ((rc = fetch_header(c, &h))) return rc;
-    const size_t nb = (size_t)(h.nu > 1 ? h.nu - 1 : 0) * 16, tb = (size_t)h.n * 48;
+    const size_t nb = (size_t)(h.quality ? (h.n > 1 ? h.n - 1 : 0) : (h.nu > 1 ? h.nu - 1 : 0)) * 16, tb = (size_t)h.n * 48;
     uint8_t* d = (uint8_t*)dev_dst;
     BIHRT_CUDA(c, cudaMemcpyAsync(d, c->d_hdr, 64, cudaMemcpyDeviceToDevice, c->stream));
     if (nb) BIHRT_CUDA(c, cudaMemcpyAsync(d + 64, c->d_nodes, nb, cudaMemcpyDeviceToDevice, c->stream));
@@ -814,7 +848,7 @@ int bihrt_bih_import(bihrt_ctx* c, const void* dev_src, uint64_t bytes) {
     BihHeader h;
     BIHRT_CUDA(c, cudaMemcpyAsync(&h, dev_src, 64, cudaMemcpyDeviceToHost, c->stream));
     BIHRT_CUDA(c, cudaStreamSynchronize(c->stream));
-    const size_t nb = (size_t)(h.nu > 1 ? h.nu - 1 : 0) * 16, tb = (size_t)h.n * 48;
+    const size_t nb = (size_t)(h.quality ? (h.n > 1 ? h.n - 1 : 0) : (h.nu > 1 ? h.nu - 1 : 0)) * 16, tb = (size_t)h.n * 48;
     if (h.nu > h.n || bytes < 64 + nb + tb) return bihrt_fail(c, BIHRT_ERR_INVALID, "blob truncated or corrupt");
     int rc = ensure_capacity(c, h.n, false);
     if (rc) return rc;
@@ -827,7 +861,7 @@ int bihrt_bih_import(bihrt_ctx* c, const void* dev_src, uint64_t bytes) {
     BIHRT_CUDA(c, cudaMemcpyAsync(c->d_hdr, s, 64, cudaMemcpyDeviceToDevice, c->stream));
     if (nb) BIHRT_CUDA(c, cudaMemcpyAsync(c->d_nodes, s + 64, nb, cudaMemcpyDeviceToDevice, c->stream));
     if (tb) BIHRT_CUDA(c, cudaMemcpyAsync(c->d_tris, s + 64 + nb, tb, cudaMemcpyDeviceToDevice, c->stream));
-    c->n = h.n; c->built = true; c->build_timed = false; c->topology_valid = false;
+    c->n = h.n; c->built = true; c->build_timed = false; c->topology_valid = false; c->built_quality = h.quality != 0;
     return BIHRT_OK;
 }
 
@@ -884,6 +918,7 @@ int bihrt_bih_copy(bihrt_ctx* dst, bihrt_ctx* src) {
     BIHRT_CUDA(dst, cudaStreamWaitEvent(src->stream, done, 0));
     BIHRT_CUDA(dst, cudaSetDevice(dst->device));
     cudaEventDestroy(done);
+    dst->opt_morton_bits = src->built_quality ? 63 : 30;         // the replica is a tree of the builder's kind
     return bihrt_bih_adopt(dst, src->n);
 }
 
@@ -891,6 +926,8 @@ int bihrt_bih_adopt(bihrt_ctx* c, int64_t n) {
     ENTER(c);
     if (n != c->n || !c->d_blob) return bihrt_fail(c, BIHRT_ERR_STATE, "bihrt_bih_adopt(%lld) without a matching bihrt_bih_region", (long long)n);
     c->built = true; c->build_timed = false; c->topology_valid = false;
+    c->built_quality = c->opt_morton_bits == 63;                 // (the kernel refuses a tree of the other kind: see check_status)
+    if (c->h_status) *c->h_status = 0;
     return BIHRT_OK;
 }
 

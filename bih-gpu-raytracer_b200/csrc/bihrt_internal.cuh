@@ -51,7 +51,8 @@ struct BihHeader {
     float    hi[3];
     uint32_t status;     // 0 ok, !=0 device watchdog
     uint32_t root_axis;  // split axis of node 0
-    uint32_t pad[6];
+    uint32_t quality;    // 0: the reference's tree (parity layout, nu - 1 nodes); 1: quality-mode tree (node slots up to n - 1, deeper)
+    uint32_t pad[5];
 };
 static_assert(sizeof(BihHeader) == 64, "header is one 64-byte line");
 
@@ -81,6 +82,8 @@ struct bihrt_ctx {
 
     // build scratch (all sized by cap_n)
     uint32_t *d_keys[2] = {nullptr, nullptr}, *d_vals[2] = {nullptr, nullptr};
+    uint64_t *d_keys64[2] = {nullptr, nullptr};   // quality mode: 63-bit Morton keys (allocated on first use)
+    uint32_t *d_lookback_q = nullptr; size_t lookback_q_words = 0;
     uint32_t *d_umc = nullptr;        // unique codes [nu]
     uint32_t *d_first = nullptr;      // first slot of each leaf [nu+1]
     uint32_t *d_hist = nullptr;       // 4 x 256 digit histograms + tile counters + misc
@@ -130,6 +133,9 @@ struct bihrt_ctx {
     int64_t kernel_launches = 0;
     int opt_build_graph = 1;            // replay the build as a captured CUDA graph
     cudaGraphExec_t build_graph_exec = nullptr; int64_t build_graph_n = -1, build_graph_launches = 0;
+    int opt_morton_bits = 30;   // 30: the reference's grid (parity path); 63: quality mode (non-parity)
+    int opt_leaf_cap = 4;       // quality mode: a subtree of at most this many triangles becomes one leaf
+    bool built_quality = false; // the BIH in the blob is a quality-mode tree (deeper: the traversal needs the long stack, and no reference quirks)
     int opt_debug_trip_watchdog = 0;   // tests: the next build reports this watchdog status (as if a sort pass had timed out)
     int opt_profile = 0;    // record an event after every build stage (bihrt_get_stat "build_stage_us_<i>")
     cudaEvent_t prof_ev[BIHRT_PROF_EVENTS] = {};
@@ -142,6 +148,7 @@ int  bihrt_fail(bihrt_ctx* c, int code, const char* fmt, ...);
 
 // build.cu
 int bihrt_build_launch(bihrt_ctx* c);
+int bihrt_build_launch_q(bihrt_ctx* c);
 int bihrt_refit_launch(bihrt_ctx* c);
 // trace.cu
 struct TraceArgs {
@@ -159,6 +166,7 @@ struct TraceArgs {
     int gshift;             // the samples of a pixel are spread over 2^gshift consecutive lanes (camera modes)
     uint32_t* fb;
     unsigned long long* counters; uint32_t* work;
+    uint32_t* status_map;   // mapped host word for device-detected errors (tree of the wrong kind for this kernel)
     int refill_threshold;   // lanes whose ray ended wait until this many are idle (or nobody is busy)
     int refill_incoherent;  // threshold used instead for ray-list packets with mixed direction signs
     int chunk_items;        // work items (rays / pixels) a warp takes from the global counter at once (queues == 1)

@@ -86,18 +86,18 @@ __device__ __forceinline__ void minmax3(float a, float b, float c, float& mn, fl
 }
 
 // d_hist layout (uint32 words)
-#define H_HIST      0        // 4 x 256 digit counts
-#define H_TILECTR   1024     // [0..3] onesweep tile counters, [4] rle tile counter
-#define H_WORDS     1040
+#define H_HIST      0        // up to 8 x 256 digit counts (4 passes for the 30-bit keys, 8 for the 63-bit keys of the quality mode)
+#define H_TILECTR   2048     // [0..7] onesweep tile counters, [8] rle tile counter
+#define H_WORDS     2064
 
 // ------------------------------------------------------------------------------------------
 // also clears the look-back words of the four sort passes (one launch instead of a kernel + a memset node)
-__global__ void __launch_bounds__(256) k_init(uint32_t* hist, uint32_t* enc, BihHeader* hdr, uint32_t n, uint4* __restrict__ lookback, uint32_t lb_vec4, uint32_t status0) {
+__global__ void __launch_bounds__(256) k_init(uint32_t* hist, uint32_t* enc, BihHeader* hdr, uint32_t n, uint4* __restrict__ lookback, uint32_t lb_vec4, uint32_t status0, uint32_t quality) {
     for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < lb_vec4; i += gridDim.x * 256u) lookback[i] = make_uint4(0u, 0u, 0u, 0u);
     if (blockIdx.x != 0) return;
     for (int i = threadIdx.x; i < H_WORDS; i += blockDim.x) hist[i] = 0;
     if (threadIdx.x < 3) { enc[threadIdx.x] = 0xFFFFFFFFu; enc[3 + threadIdx.x] = 0u; }
-    if (threadIdx.x == 0) { hdr->n = n; hdr->nu = 0; hdr->status = status0; hdr->root_axis = 0; }
+    if (threadIdx.x == 0) { hdr->n = n; hdr->nu = 0; hdr->status = status0; hdr->root_axis = 0; hdr->quality = quality; }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -238,20 +238,24 @@ __global__ void __launch_bounds__(256) k_morton(const float* __restrict__ tri, u
 // ------------------------------------------------------------------------------------------
 #define OS_THREADS 256
 #define OS_ITEMS   16
-#define OS_TILE    (OS_THREADS * OS_ITEMS)      // 4096 keys
+#define OS_TILE    (OS_THREADS * OS_ITEMS)      // 4096 keys (32-bit keys; the 64-bit keys of the quality mode use 8 items = 2048 keys)
+#define OS_ITEMS64 8
+#define OS_TILE64  (OS_THREADS * OS_ITEMS64)
 #define LB_FLAG_AGG   0x40000000u
 #define LB_FLAG_INCL  0x80000000u
 #define LB_MASK       0x3FFFFFFFu
 #define SPIN_LIMIT    (1u << 22)
 
-template <bool FIRST>
-__global__ void __launch_bounds__(OS_THREADS) k_onesweep(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
-                                                         uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
+template <typename K, int ITEMS, bool FIRST>
+__global__ void __launch_bounds__(OS_THREADS) k_onesweep(const K* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                                                         K* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
                                                          uint32_t n, int pass, uint32_t* __restrict__ hist,
                                                          uint32_t* __restrict__ lookback, BihHeader* hdr) {
+    constexpr int OS_ITEMS_ = ITEMS;
+    constexpr uint32_t OS_TILE_ = OS_THREADS * ITEMS;
     __shared__ uint32_t s_whist[8][256];
-    __shared__ uint32_t s_keys[OS_TILE];
-    __shared__ uint32_t s_vals[OS_TILE];
+    __shared__ K s_keys[OS_TILE_];
+    __shared__ uint32_t s_vals[OS_TILE_];
     __shared__ uint32_t s_binstart[256];
     __shared__ uint32_t s_goff[256];
     __shared__ uint32_t s_w[8];
@@ -262,24 +266,24 @@ __global__ void __launch_bounds__(OS_THREADS) k_onesweep(const uint32_t* __restr
     for (int i = tid; i < 8 * 256; i += OS_THREADS) (&s_whist[0][0])[i] = 0;
     __syncthreads();
     const uint32_t tile = s_tile;
-    const uint32_t tile_base = tile * OS_TILE;
-    const uint32_t valid = min((uint32_t)OS_TILE, n - tile_base);
+    const uint32_t tile_base = tile * OS_TILE_;
+    const uint32_t valid = min((uint32_t)OS_TILE_, n - tile_base);
 
     // global base of each digit for this pass = exclusive scan of the whole-array histogram
     uint32_t tot;
     uint32_t gbase = block_excl_scan_256(hist[H_HIST + pass * 256 + tid], s_w, &tot);
 
-    uint32_t key[OS_ITEMS], rank[OS_ITEMS];
-    const uint32_t i0 = tile_base + warp * (32 * OS_ITEMS) + lane;
+    K key[OS_ITEMS_]; uint32_t rank[OS_ITEMS_];
+    const uint32_t i0 = tile_base + warp * (32 * OS_ITEMS_) + lane;
 #pragma unroll
-    for (int i = 0; i < OS_ITEMS; i++) {
+    for (int i = 0; i < OS_ITEMS_; i++) {
         uint32_t gi = i0 + i * 32;
-        key[i] = gi < n ? __ldcs(keys_in + gi) : 0xFFFFFFFFu;
+        key[i] = gi < n ? __ldcs(keys_in + gi) : ~(K)0;
     }
     const uint32_t lt = (1u << lane) - 1u;
 #pragma unroll
-    for (int i = 0; i < OS_ITEMS; i++) {
-        uint32_t d = (key[i] >> shift) & 255u;
+    for (int i = 0; i < OS_ITEMS_; i++) {
+        uint32_t d = (uint32_t)(key[i] >> shift) & 255u;
         uint32_t peers = __match_any_sync(FULL, d);
         int leader = __ffs(peers) - 1;
         uint32_t old = 0;
@@ -296,8 +300,8 @@ __global__ void __launch_bounds__(OS_THREADS) k_onesweep(const uint32_t* __restr
     for (int w = 0; w < 8; w++) { uint32_t c = s_whist[w][tid]; s_whist[w][tid] = cnt; cnt += c; }
     uint32_t binstart = block_excl_scan_256(cnt, s_w, &tot);
     s_binstart[tid] = binstart;
-    // padding keys (0xFFFFFFFF, digit 255 in every pass) sit at the very end of the tile: not counted
-    uint32_t cnt_real = cnt - ((tid == 255) ? ((uint32_t)OS_TILE - valid) : 0u);
+    // padding keys (all ones, digit 255 in every pass; a valid 63-bit key has digit <= 127 in its last pass) sit at the very end of the tile: not counted
+    uint32_t cnt_real = cnt - ((tid == 255) ? ((uint32_t)OS_TILE_ - valid) : 0u);
 
     // decoupled look-back: exclusive count of this digit over all previous tiles
     uint32_t excl = 0;
@@ -323,8 +327,8 @@ __global__ void __launch_bounds__(OS_THREADS) k_onesweep(const uint32_t* __restr
 
     // tile-local reorder through shared memory so the global scatter is coalesced per digit
 #pragma unroll
-    for (int i = 0; i < OS_ITEMS; i++) {
-        uint32_t d = (key[i] >> shift) & 255u;
+    for (int i = 0; i < OS_ITEMS_; i++) {
+        uint32_t d = (uint32_t)(key[i] >> shift) & 255u;
         uint32_t pos = s_binstart[d] + s_whist[warp][d] + rank[i];
         s_keys[pos] = key[i];
         uint32_t gi = i0 + i * 32;
@@ -335,11 +339,11 @@ __global__ void __launch_bounds__(OS_THREADS) k_onesweep(const uint32_t* __restr
     }
     __syncthreads();
 #pragma unroll
-    for (int k = 0; k < OS_ITEMS; k++) {
+    for (int k = 0; k < OS_ITEMS_; k++) {
         uint32_t j = tid + k * OS_THREADS;
         if (j < valid) {
-            uint32_t kk = s_keys[j];
-            uint32_t dst = s_goff[(kk >> shift) & 255u] + j;
+            K kk = s_keys[j];
+            uint32_t dst = s_goff[(uint32_t)(kk >> shift) & 255u] + j;
             keys_out[dst] = kk;
             vals_out[dst] = s_vals[j];
         }
@@ -485,7 +489,7 @@ __device__ __forceinline__ void heap_reduce_block(float r[6], float (*s)[8], flo
 // Leaf-ordered triangle records + bottom heap levels: one thread per sorted slot gathers its input triangle
 // (36 B), writes the 48-byte record (coalesced) and the triangle's AABB (std::minmax semantics of
 // R/src/App.cpp:123-127) as heap level 0.  end-of-leaf = the next slot has a different Morton code.
-template <bool RLE>
+template <bool RLE, bool QUALITY>
 __global__ void __launch_bounds__(256) k_reorder(const float* __restrict__ tri_in, const uint32_t* __restrict__ idx_sorted,
                                                  const uint32_t* __restrict__ keys_sorted, uint32_t n, BihTri* __restrict__ tris,
                                                  float* __restrict__ heaps, uint32_t P, const uint32_t* __restrict__ tile_off,
@@ -501,8 +505,11 @@ __global__ void __launch_bounds__(256) k_reorder(const float* __restrict__ tri_i
         float v[9];
 #pragma unroll
         for (int i = 0; i < 9; i++) v[i] = __ldg(t + i);
-        key = keys_sorted[j];
-        const uint32_t last = (j + 1 == n || keys_sorted[j + 1] != key) ? 1u : 0u;
+        uint32_t last = 0;                                   // quality mode: leaves are marked by k_nodes_q
+        if (!QUALITY) {
+            key = keys_sorted[j];
+            last = (j + 1 == n || keys_sorted[j + 1] != key) ? 1u : 0u;
+        }
         if (RLE) head = (j == 0 || keys_sorted[j - 1] != key) ? 1u : 0u;
         float4* dst = reinterpret_cast<float4*>(tris + j);
         __stcs(dst, make_float4(v[0], v[1], v[2], __fsub_rn(v[3], v[0])));
@@ -604,6 +611,168 @@ __global__ void __launch_bounds__(128) k_nodes(const uint32_t* __restrict__ umc,
     if (idx == 0) hdr->root_axis = (uint32_t)axis;
 }
 
+// ==========================================================================================
+// QUALITY MODE (NOT a parity path, reported separately).  The reference quantises the triangle
+// centres to a 10-bit grid per axis (R/src/Renderer.cpp:116-136) and makes every occupied grid cell a leaf
+// (R/src/CUDAKernels.cu:206-224): at 10 M triangles a ray tests 24 triangles and the leaves hold up to hundreds.  Here:
+//   * 21 bits per axis -> 63-bit Morton keys, 8 x 8-bit passes of the same onesweep sort;
+//   * ties broken by the sorted position (Karras 2012, section 4), so the radix tree is built over all n triangles;
+//   * a subtree of at most `leaf_cap` triangles becomes ONE leaf (a contiguous slot range, as in the parity layout);
+//   * clip planes by the same heap range queries, so every plane bounds its subtree and the traversal kernel is the same.
+// Node i is still the Karras node i; nodes inside a collapsed subtree are simply never written or referenced.
+// ==========================================================================================
+__device__ __forceinline__ uint64_t expand_bits21(uint32_t v) {
+    uint64_t x = v & 0x1fffffu;
+    x = (x | x << 32) & 0x001f00000000ffffull;
+    x = (x | x << 16) & 0x001f0000ff0000ffull;
+    x = (x | x << 8) & 0x100f00f00f00f00full;
+    x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+    x = (x | x << 2) & 0x1249249249249249ull;
+    return x;
+}
+__device__ __forceinline__ uint64_t morton_axis21(float mn, float mx, float slo, float shi) {
+    const float centre = __fmul_rn(__fadd_rn(mn, mx), 0.5f);
+    const float nrm = __fdiv_rn(__fsub_rn(centre, slo), __fsub_rn(shi, slo));
+    const float q = fminf(fmaxf(__fmul_rn(nrm, 2097152.0f), 0.0f), 2097151.0f);
+    return expand_bits21(__float2uint_rz(q));
+}
+__device__ __forceinline__ uint64_t morton63_of_tri(const float* t, const float slo[3], const float shi[3]) {
+    float mn, mx;
+    minmax3(t[0], t[3], t[6], mn, mx); const uint64_t xx = morton_axis21(mn, mx, slo[0], shi[0]);
+    minmax3(t[1], t[4], t[7], mn, mx); const uint64_t yy = morton_axis21(mn, mx, slo[1], shi[1]);
+    minmax3(t[2], t[5], t[8], mn, mx); const uint64_t zz = morton_axis21(mn, mx, slo[2], shi[2]);
+    return (xx << 2) | (yy << 1) | zz;
+}
+
+__global__ void __launch_bounds__(256) k_morton_q(const float* __restrict__ tri, uint32_t n, const uint32_t* __restrict__ enc,
+                                                  uint64_t* __restrict__ keys, uint32_t* __restrict__ hist, BihHeader* hdr) {
+    __shared__ uint32_t s_hist[8 * 256];
+    for (int i = threadIdx.x; i < 2048; i += 256) s_hist[i] = 0;
+    float slo[3], shi[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) { slo[k] = dec_float(enc[k]); shi[k] = dec_float(enc[3 + k]); }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) { hdr->lo[k] = slo[k]; hdr->hi[k] = shi[k]; }
+    }
+    __syncthreads();
+    for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < n; i += gridDim.x * 256u) {
+        float t[9];
+#pragma unroll
+        for (int k = 0; k < 9; k++) t[k] = __ldcs(tri + (size_t)i * 9 + k);
+        const uint64_t code = morton63_of_tri(t, slo, shi);
+        keys[i] = code;
+#pragma unroll
+        for (int p = 0; p < 8; p++) atomicAdd(&s_hist[p * 256 + ((uint32_t)(code >> (8 * p)) & 255u)], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2048; i += 256) { const uint32_t v = s_hist[i]; if (v) atomicAdd(&hist[H_HIST + i], v); }
+}
+
+// length of the common prefix of the (key, position) pairs i and j: 64 key bits, then 32 position bits
+__device__ __forceinline__ int delta_q(const uint64_t* __restrict__ keys, int n, uint64_t ki, int i, int j) {
+    if (j < 0 || j > n - 1) return -1;
+    const uint64_t x = ki ^ __ldg(keys + j);
+    return x ? __clzll((long long)x) : 64 + __clz(i ^ j);
+}
+// split axis of the bit at prefix length p: key bit 62 (p = 1) is x's top bit; position bits keep cycling
+__device__ __forceinline__ uint32_t axis_of_prefix(int p) { return (uint32_t)((p + 2) % 3); }
+
+__global__ void __launch_bounds__(128) k_nodes_q(const uint64_t* __restrict__ keys, uint32_t n_, uint32_t cap, BihHeader* hdr,
+                                                 const float* __restrict__ heaps, uint32_t P, BihNode* __restrict__ nodes,
+                                                 BihTri* __restrict__ tris, uint32_t* __restrict__ status_map) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = (int)n_;
+    if (idx == 0) *status_map = hdr->status;
+    if (n_ <= cap) {                                       // the whole scene is one leaf
+        if (idx == 0) { hdr->nu = 1; hdr->root_axis = 0; tris[n - 1].last = 1u; }
+        return;
+    }
+    uint32_t made = 0;                                     // leaves this thread creates
+    if (idx <= n - 2) {
+        const uint64_t cur = __ldg(keys + idx);
+        auto lcp = [&](int j) -> int { return delta_q(keys, n, cur, idx, j); };
+        const int d = lcp(idx + 1) > lcp(idx - 1) ? 1 : -1;
+        const int lcp_min = lcp(idx - d);
+        int l_max = 1;
+        do { l_max *= 2; } while (lcp(idx + l_max * d) > lcp_min);
+        int l = 0;
+        for (int t = l_max / 2; t >= 1; t /= 2)
+            if (lcp(idx + (l + t) * d) > lcp_min) l += t;
+        const int other_end = idx + l * d;
+        const int a = min(idx, other_end), b = max(idx, other_end);
+        // nodes inside a collapsed subtree are never referenced: nothing to do (the root always has more than cap triangles)
+        if ((uint32_t)(b - a + 1) > cap || idx == 0) {
+            const int lcp_ends = lcp(other_end);
+            int s = 0;
+            for (int t = l;;) {
+                t = (t + 1) >> 1;
+                if (lcp(idx + (s + t) * d) > lcp_ends) s += t;
+                if (t == 1) break;
+            }
+            const int split = idx + s * d + min(d, 0);
+            const uint64_t ka = __ldg(keys + a), ks = __ldg(keys + split), ks1 = __ldg(keys + split + 1), kb = __ldg(keys + b);
+            auto pre = [&](uint64_t x, uint64_t y, int i, int j) -> int { const uint64_t z = x ^ y; return z ? __clzll((long long)z) : 64 + __clz(i ^ j); };
+            const uint32_t axis = axis_of_prefix(pre(ks, ks1, split, split + 1));
+            const bool leaf_l = (uint32_t)(split - a + 1) <= cap, leaf_r = (uint32_t)(b - split) <= cap;
+            const uint32_t ref_l = leaf_l ? BIH_REF_LEAFREF(a) : BIH_REF_NODE(split, axis_of_prefix(pre(ka, ks, a, split)));
+            const uint32_t ref_r = leaf_r ? BIH_REF_LEAFREF(split + 1) : BIH_REF_NODE(split + 1, axis_of_prefix(pre(ks1, kb, split + 1, b)));
+            if (leaf_l) { tris[split].last = 1u; made++; }
+            if (leaf_r) { tris[b].last = 1u; made++; }
+            const float* hmax = heaps + (size_t)axis * 2 * P;
+            const float* hmin = heaps + (size_t)(3 + axis) * 2 * P;
+            float cl0 = -INFINITY, cl1 = INFINITY;
+            uint32_t l0 = a + P, r0 = split + 1 + P, l1 = split + 1 + P, r1 = b + 1 + P;
+            while (l0 < r0 || l1 < r1) {
+                float a0 = -INFINITY, b0 = -INFINITY, a1 = INFINITY, b1 = INFINITY;
+                if (l0 < r0) { if (l0 & 1u) a0 = __ldg(hmax + l0++); if (r0 & 1u) b0 = __ldg(hmax + --r0); l0 >>= 1; r0 >>= 1; }
+                if (l1 < r1) { if (l1 & 1u) a1 = __ldg(hmin + l1++); if (r1 & 1u) b1 = __ldg(hmin + --r1); l1 >>= 1; r1 >>= 1; }
+                cl0 = fmaxf(cl0, fmaxf(a0, b0));
+                cl1 = fminf(cl1, fminf(a1, b1));
+            }
+            *reinterpret_cast<float4*>(nodes + idx) = make_float4(cl0, cl1, __uint_as_float(ref_l), __uint_as_float(ref_r));
+            if (idx == 0) hdr->root_axis = axis;
+        }
+    }
+    made = __reduce_add_sync(FULL, made);
+    if ((threadIdx.x & 31) == 0 && made) atomicAdd(&hdr->nu, made);      // leaves (k_init zeroed it)
+}
+
+int bihrt_build_launch_q(bihrt_ctx* c) {
+    const uint32_t n = (uint32_t)c->n;
+    cudaStream_t st = c->stream;
+    const uint32_t os_tiles = (n + OS_TILE64 - 1) / OS_TILE64;
+    const size_t lb_words = (size_t)8 * os_tiles * 256;
+    if (lb_words > c->lookback_q_words || !c->d_keys64[0]) return bihrt_fail(c, BIHRT_ERR_INTERNAL, "quality-mode scratch not allocated");
+    const uint32_t lb_vec4 = (uint32_t)((lb_words + 3) / 4);
+    k_init<<<(int)max(1u, min((uint32_t)c->sm_count, (lb_vec4 + 1023u) / 1024u)), 256, 0, st>>>(c->d_hist, c->d_scenebox_enc, c->d_hdr, n,
+                                                                                      reinterpret_cast<uint4*>(c->d_lookback_q), lb_vec4, (uint32_t)c->opt_debug_trip_watchdog, 1u);
+    const int stream_grid = (int)max(1u, min((uint32_t)(c->sm_count * 3), ((n >> 2) + 255) / 256));
+    k_scene_box<<<stream_grid, 256, 0, st>>>(c->d_tri_in, n, c->d_scenebox_enc);
+    k_morton_q<<<(int)max(1u, min((uint32_t)(c->sm_count * 4), (n + 255) / 256)), 256, 0, st>>>(c->d_tri_in, n, c->d_scenebox_enc, c->d_keys64[0], c->d_hist, c->d_hdr);
+    int cur = 0;
+    for (int pass = 0; pass < 8; pass++) {
+        uint32_t* lb = c->d_lookback_q + (size_t)pass * os_tiles * 256;
+        if (pass == 0)
+            k_onesweep<uint64_t, OS_ITEMS64, true><<<os_tiles, OS_THREADS, 0, st>>>(c->d_keys64[cur], nullptr, c->d_keys64[cur ^ 1], c->d_vals[cur ^ 1], n, pass, c->d_hist, lb, c->d_hdr);
+        else
+            k_onesweep<uint64_t, OS_ITEMS64, false><<<os_tiles, OS_THREADS, 0, st>>>(c->d_keys64[cur], c->d_vals[cur], c->d_keys64[cur ^ 1], c->d_vals[cur ^ 1], n, pass, c->d_hist, lb, c->d_hdr);
+        cur ^= 1;
+    }
+    uint32_t P = 256;
+    while (P < n) P <<= 1;
+    k_reorder<false, true><<<(n + 255) / 256, 256, 0, st>>>(c->d_tri_in, c->d_vals[cur], nullptr, n, c->d_tris, c->d_heaps, P, nullptr, nullptr, nullptr);
+    int launches = 0;
+    for (uint32_t lvl = P >> 8, used = (n + 255) / 256; lvl > 1; lvl >>= 8, used = (used + 255) / 256) {
+        k_heap_up<<<(used + 255) / 256, 256, 0, st>>>(c->d_heaps, P, lvl, used);
+        launches++;
+    }
+    k_nodes_q<<<(n + 127) / 128, 128, 0, st>>>(c->d_keys64[cur], n, (uint32_t)c->opt_leaf_cap, c->d_hdr, c->d_heaps, P, c->d_nodes, c->d_tris, c->d_status_map);
+    c->kernel_launches += 13 + launches;
+    BIHRT_CUDA(c, cudaGetLastError());
+    return BIHRT_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 int bihrt_build_launch(bihrt_ctx* c) {
     const uint32_t n = (uint32_t)c->n;
@@ -619,7 +788,7 @@ int bihrt_build_launch(bihrt_ctx* c) {
     PROF_MARK();
     const uint32_t lb_vec4 = (uint32_t)((lb_words + 3) / 4);        // the buffer is allocated with 16 spare words
     k_init<<<(int)max(1u, min((uint32_t)c->sm_count, (lb_vec4 + 1023u) / 1024u)), 256, 0, st>>>(c->d_hist, c->d_scenebox_enc, c->d_hdr, n,
-                                                                                      reinterpret_cast<uint4*>(c->d_lookback), lb_vec4, (uint32_t)c->opt_debug_trip_watchdog);
+                                                                                      reinterpret_cast<uint4*>(c->d_lookback), lb_vec4, (uint32_t)c->opt_debug_trip_watchdog, 0u);
     PROF_MARK();   // 1: after init + memsets
     const int stream_grid = (int)max(1u, min((uint32_t)(c->sm_count * 3), ((n >> 2) + 255) / 256));
     k_scene_box<<<stream_grid, 256, 0, st>>>(c->d_tri_in, n, c->d_scenebox_enc);
@@ -630,9 +799,9 @@ int bihrt_build_launch(bihrt_ctx* c) {
     for (int pass = 0; pass < 4; pass++) {
         uint32_t* lb = c->d_lookback + (size_t)pass * os_tiles * 256;
         if (pass == 0)
-            k_onesweep<true><<<os_tiles, OS_THREADS, 0, st>>>(c->d_keys[cur], nullptr, c->d_keys[cur ^ 1], c->d_vals[cur ^ 1], n, pass, c->d_hist, lb, c->d_hdr);
+            k_onesweep<uint32_t, OS_ITEMS, true><<<os_tiles, OS_THREADS, 0, st>>>(c->d_keys[cur], nullptr, c->d_keys[cur ^ 1], c->d_vals[cur ^ 1], n, pass, c->d_hist, lb, c->d_hdr);
         else
-            k_onesweep<false><<<os_tiles, OS_THREADS, 0, st>>>(c->d_keys[cur], c->d_vals[cur], c->d_keys[cur ^ 1], c->d_vals[cur ^ 1], n, pass, c->d_hist, lb, c->d_hdr);
+            k_onesweep<uint32_t, OS_ITEMS, false><<<os_tiles, OS_THREADS, 0, st>>>(c->d_keys[cur], c->d_vals[cur], c->d_keys[cur ^ 1], c->d_vals[cur ^ 1], n, pass, c->d_hist, lb, c->d_hdr);
         cur ^= 1;
         PROF_MARK();   // 4..7: after each sort pass
     }
@@ -644,7 +813,7 @@ int bihrt_build_launch(bihrt_ctx* c) {
     // heaps are padded to a power of two >= n (Nu <= n is only known on the device)
     uint32_t P = 256;
     while (P < n) P <<= 1;
-    k_reorder<true><<<(n + 255) / 256, 256, 0, st>>>(c->d_tri_in, c->d_vals[cur], c->d_keys[cur], n, c->d_tris, c->d_heaps, P, tile_cnt, c->d_umc, c->d_first);
+    k_reorder<true, false><<<(n + 255) / 256, 256, 0, st>>>(c->d_tri_in, c->d_vals[cur], c->d_keys[cur], n, c->d_tris, c->d_heaps, P, tile_cnt, c->d_umc, c->d_first);
     PROF_MARK();   // 9: after reorder + slot boxes + leaves
     int launches = 0;
     for (uint32_t lvl = P >> 8, used = (n + 255) / 256; lvl > 1; lvl >>= 8, used = (used + 255) / 256) {   // level with `lvl` elements
@@ -684,7 +853,7 @@ int bihrt_refit_launch(bihrt_ctx* c) {
     k_refit_init<<<1, 32, 0, st>>>(c->d_scenebox_enc);
     k_scene_box<<<stream_grid, 256, 0, st>>>(c->d_tri_in, n, c->d_scenebox_enc);
     k_refit_box<<<1, 32, 0, st>>>(c->d_scenebox_enc, c->d_hdr);
-    k_reorder<false><<<(n + 255) / 256, 256, 0, st>>>(c->d_tri_in, c->d_vals[0], c->d_keys[0], n, c->d_tris, c->d_heaps, P, nullptr, nullptr, nullptr);
+    k_reorder<false, false><<<(n + 255) / 256, 256, 0, st>>>(c->d_tri_in, c->d_vals[0], c->d_keys[0], n, c->d_tris, c->d_heaps, P, nullptr, nullptr, nullptr);
     int launches = 0;
     for (uint32_t lvl = P >> 8, used = (n + 255) / 256; lvl > 1; lvl >>= 8, used = (used + 255) / 256) {
         k_heap_up<<<(used + 255) / 256, 256, 0, st>>>(c->d_heaps, P, lvl, used);

@@ -29,7 +29,8 @@
 #include <float.h>
 
 #define FULL 0xffffffffu
-#define STACK_DEPTH 32          // <= 31 items: one per Morton bit on a root-to-leaf path, plus one
+#define STACK_DEPTH_PARITY  32  // <= 31 items: one per Morton bit on a root-to-leaf path, plus one
+#define STACK_DEPTH_QUALITY 96  // quality mode: 63 key bits + up to 29 position bits of tie-breaking
 #define NONE 0xFFFFFFFFu        // "no item": leaf bit set, never a valid slot
 #ifndef TRACE_THREADS
 #define TRACE_THREADS 128
@@ -106,8 +107,12 @@ __device__ __forceinline__ void test_leaf(const char* __restrict__ first_tri, fl
 // ------------------------------------------------------------------------------------------
 // WALK > 0: the node phase takes exactly WALK steps between two votes and always votes (the shipped setting,
 // unrolled); WALK == 0: both come from the launch arguments (tuning / tests).
-template <int MODE, bool COUNTED, int WALK>
+// Q: the BIH is a quality-mode tree (63-bit keys, capped leaves; csrc/build.cu): long stack, and the closed tight-interval
+// tests alone decide -- the reference's extra strict test (rMin < t[near], :292), which the parity path reproduces together
+// with the hits it loses on axis-aligned geometry, is dropped.
+template <int MODE, bool COUNTED, int WALK, bool Q>
 __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(TraceArgs a) {
+    constexpr int STACK_DEPTH = Q ? STACK_DEPTH_QUALITY : STACK_DEPTH_PARITY;
     // per-axis ray constants (origin, 1/dir), one row of 3 float2 per thread: 24-byte stride keeps a
     // half-warp's 64-bit accesses on distinct banks when the lanes agree on the axis
     __shared__ float2 s_ray[TRACE_THREADS * 3];
@@ -119,6 +124,10 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
     const BihTri* __restrict__ tris = a.tris;
     const uint32_t nu = a.hdr->nu;
     if (a.hdr->status != 0) return;             // the build's device watchdog tripped: trace nothing rather than garbage (the host reports it)
+    if ((a.hdr->quality != 0) != Q) {           // a tree of the other kind (a replica adopted without the matching morton_bits option)
+        if (blockIdx.x == 0 && threadIdx.x == 0 && a.status_map) *a.status_map = 0x100u;
+        return;
+    }
     const float blo[3] = { a.hdr->lo[0], a.hdr->lo[1], a.hdr->lo[2] }, bhi[3] = { a.hdr->hi[0], a.hdr->hi[1], a.hdr->hi[2] };
     uint32_t nnodes = 0, ntris = 0, maxsp = 0;
     uint32_t wnode = 0, wleaf = 0;              // COUNTED: warp-level executions of the node step / the triangle test (SIMD efficiency = lane steps / 32 / these)
@@ -430,7 +439,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
                 const uint32_t refn = neg ? rr : rl, reff = neg ? rl : rr;
                 const float nMax = fminf(pMax, tn);
                 const float fMin = fmaxf(pMin, tf);
-                const bool go_near = (rMin < tn) && (pMin <= nMax);   // reference's strict test (:292) + closed tight interval
+                const bool go_near = (Q || rMin < tn) && (pMin <= nMax);   // reference's strict test (:292) + closed tight interval
                 const bool go_far = (fMin <= pMax);
                 if (go_near && go_far) {
                     // near before far, except a far LEAF next to a near NODE is tested first (:344-349)
@@ -595,15 +604,15 @@ int bihrt_resolve_launch(bihrt_ctx* c, uint32_t* fb, int npix, int spp) {
 #ifndef TRACE_WALK
 #define TRACE_WALK 3
 #endif
-template <int MODE, bool COUNTED, int WALK>
+template <int MODE, bool COUNTED, int WALK, bool Q = false>
 static int launch(bihrt_ctx* c, const TraceArgs& a) {
     int per_sm = c->opt_trace_blocks_per_sm;
     if (per_sm <= 0) {
-        BIHRT_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<MODE, COUNTED, WALK>, TRACE_THREADS, 0));
+        BIHRT_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<MODE, COUNTED, WALK, Q>, TRACE_THREADS, 0));
         if (per_sm < 1) per_sm = 1;
     }
     BIHRT_CUDA(c, cudaMemsetAsync(a.work, 0, 4 * 1024, c->stream));
-    k_trace<MODE, COUNTED, WALK><<<c->sm_count * per_sm, TRACE_THREADS, 0, c->stream>>>(a);
+    k_trace<MODE, COUNTED, WALK, Q><<<c->sm_count * per_sm, TRACE_THREADS, 0, c->stream>>>(a);
     c->kernel_launches += 1;
     BIHRT_CUDA(c, cudaGetLastError());
     return BIHRT_OK;
@@ -672,6 +681,20 @@ int bihrt_trace_launch(bihrt_ctx* c, const TraceArgs& a_in, int mode, bool count
     }
     const bool shipped = a.vote_wait != 0 && a.vote_walk == TRACE_WALK;    // the unrolled instantiation
     int rc = BIHRT_ERR_INVALID;
+    a.status_map = c->d_status_map;
+    if (c->built_quality) {
+        // quality-mode tree: the shipped schedule only (3 node steps per vote); the instrumented build walks one step per vote
+        TraceArgs q = a; q.vote_wait = 1; q.vote_walk = 1;
+        switch (mode * 2 + (counted ? 1 : 0)) {
+            case 0: rc = launch<0, false, TRACE_WALK, true>(c, a); break;
+            case 1: rc = launch<0, true, 0, true>(c, q); break;
+            case 2: rc = launch<1, false, TRACE_WALK, true>(c, a); break;
+            case 3: rc = launch<1, true, 0, true>(c, q); break;
+            case 4: rc = launch<2, false, TRACE_WALK, true>(c, a); break;
+            case 5: rc = launch<2, true, 0, true>(c, q); break;
+            default: return bihrt_fail(c, BIHRT_ERR_INVALID, "bad trace mode %d", mode);
+        }
+    } else
     switch (mode * 2 + (counted ? 1 : 0)) {
         case 0: rc = shipped ? launch<0, false, TRACE_WALK>(c, a) : launch<0, false, 0>(c, a); break;
         case 1: rc = launch<0, true, 0>(c, a); break;
