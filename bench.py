@@ -41,6 +41,7 @@ for _p in (ROOT, os.path.join(ROOT, "bih-gpu-raytracer_b200")):
 
 METRIC = "Mrays/s"
 L2_FLUSH_BYTES = 256 << 20          # > 126 MB L2
+NODE_BYTES = 64                     # one node record: the BIH pair of clip planes + child references (16 B) and the two children boxes (48 B)
 
 
 def log(*a):
@@ -594,7 +595,7 @@ def run_ours(args, rank, world, local_rank):
             barrier()
             res = {"triangles": n10, "rays_per_frame": rays_total, "trace_ms_max_over_ranks": t_f,
                    "mrays_s": rays_total / (t_f * 1e-3) / 1e6, "bih_broadcast_ms": t_b,
-                   "bih_blob_bytes": 64 + n10 * 64, "bih_broadcast_gb_s": (64 + n10 * 64) / (t_b * 1e-3) / 1e9,
+                   "bih_blob_bytes": 64 + n10 * (NODE_BYTES + 48), "bih_broadcast_gb_s": (64 + n10 * (NODE_BYTES + 48)) / (t_b * 1e-3) / 1e9,
                    "mrays_s_with_one_broadcast_per_frame": rays_total / ((t_f + t_b) * 1e-3) / 1e6,
                    "what": "BASELINE config 4: 9 999 392-triangle mesh, 3840x2160 x 16 spp, unit interleave over %d GPUs, BIH built on rank 0 and "
                            "replicated in place by one NCCL broadcast; L2 flushed; max over ranks" % world}
@@ -629,7 +630,7 @@ def run_ours(args, rank, world, local_rank):
         # kernel over the same frame at 1 spp (same camera, same jitter stream)
         cnt = r.render_counted(cam, W, H, spp=1, seed=1984, jitter=True)
         v_n, v_t = cnt["nodes"] / cnt["rays"], cnt["tris"] / cnt["rays"]
-        bytes_per_ray = v_n * 16 + v_t * 48 + 4.0 / spp
+        bytes_per_ray = v_n * NODE_BYTES + v_t * 48 + 4.0 / spp
         if world == 1:
             kern_s = ms_per_step * 1e-3
             achieved = bytes_per_ray * rays_total / kern_s / 1e9
@@ -719,8 +720,8 @@ def run_ours(args, rank, world, local_rank):
             cp = r.render_counted(c3, w, h, spp=s_, jitter=jit)
             _t, _s, _p, cq = r.trace(db, counted=True)
             # (the occlusion query visits fewer nodes than the closest-hit trace the counters come from: upper bound on its bytes)
-            bytes_p = cp["nodes"] * 16 + cp["tris"] * 48 + n_p * 12
-            bytes_s = cq["nodes"] * 16 + cq["tris"] * 48 + n_s * 28
+            bytes_p = cp["nodes"] * NODE_BYTES + cp["tris"] * 48 + n_p * 12
+            bytes_s = cq["nodes"] * NODE_BYTES + cq["tris"] * 48 + n_s * 28
             pk = peaks()[0]
             return {"what": label, "primary_rays": n_p, "shadow_rays": n_s,
                     "primary_mrays_s": n_p / (t_p * 1e-3) / 1e6, "shadow_occlusion_mrays_s": n_s / (t_s * 1e-3) / 1e6,
@@ -752,7 +753,7 @@ def run_ours(args, rank, world, local_rank):
                      "build_roofline_frac": len(t2) * 320 / (bms * 1e-3) / 1e9 / peaks()[0],
                      "primary_mrays_s_1080p_1spp": primary(c2, 1920, 1080, 1), "primary_mrays_s_1080p_4spp": primary(c2, 1920, 1080, 4)}
                 cc = r.render_counted(c2, 1920, 1080, spp=1)
-                bpr = cc["nodes"] / cc["rays"] * 16 + cc["tris"] / cc["rays"] * 48 + 4.0
+                bpr = cc["nodes"] / cc["rays"] * NODE_BYTES + cc["tris"] / cc["rays"] * 48 + 4.0
                 pk = peaks()[0]
                 e.update({"nodes_per_ray": cc["nodes"] / cc["rays"], "tris_per_ray": cc["tris"] / cc["rays"], "algorithmic_bytes_per_ray": bpr,
                           "roofline_frac_1080p_1spp": e["primary_mrays_s_1080p_1spp"] * 1e6 * bpr / (pk * 1e9),

@@ -51,12 +51,12 @@ static size_t lookback_words_for(int64_t n) {
     return 4 * os_tiles * 256 + rle_tiles * 8 + 16;
 }
 
-static size_t blob_capacity(int64_t n) { return 64 + (size_t)n * 16 + (size_t)n * 48 + 64; }
+static size_t blob_capacity(int64_t n) { return 64 + (size_t)n * sizeof(BihNode) + (size_t)n * 48 + 64; }
 
 static void bind_blob(bihrt_ctx* c, int64_t cap) {
     c->d_hdr = reinterpret_cast<BihHeader*>(c->d_blob);
     c->d_nodes = reinterpret_cast<BihNode*>(c->d_blob + 64);
-    c->d_tris = reinterpret_cast<BihTri*>(c->d_blob + 64 + (size_t)cap * 16);
+    c->d_tris = reinterpret_cast<BihTri*>(c->d_blob + 64 + (size_t)cap * sizeof(BihNode));
 }
 
 // GPUArrayManager::AllocateTris / AllocateMortonCodes / AllocateBIHTree (R/src/GPUArrayManager.cpp:7-91)
@@ -88,7 +88,7 @@ static int ensure_capacity(bihrt_ctx* c, int64_t n, bool with_build_scratch) {
         if ((rc = dev_alloc(c, &c->d_lookback, c->lookback_words))) return rc;
         size_t P = 256;
         while (P < (size_t)cap) P <<= 1;
-        if ((rc = dev_alloc(c, &c->d_heaps, 12 * P))) return rc;
+        if ((rc = dev_alloc(c, &c->d_heaps, 4 * P))) return rc;      // 2P entries x 2 float4
     }
     return BIHRT_OK;
 }
@@ -407,7 +407,7 @@ int bihrt_get_build_info(bihrt_ctx* c, bihrt_build_info* out) {
     if (rc) return rc;
     memset(out, 0, sizeof *out);
     out->n = h.n; out->nu = h.nu;
-    out->node_bytes = h.quality ? (h.n > 1 ? (int64_t)(h.n - 1) * 16 : 0) : (h.nu > 1 ? (int64_t)(h.nu - 1) * 16 : 0);
+    out->node_bytes = (h.quality ? (h.n > 1 ? (int64_t)(h.n - 1) : 0) : (h.nu > 1 ? (int64_t)(h.nu - 1) : 0)) * (int64_t)sizeof(BihNode);
     out->tri_bytes = (int64_t)h.n * 48;
     out->sort_passes = h.quality ? 8 : 4;
     if (c->build_timed) { float ms = 0; if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) out->last_build_ms = ms; else cudaGetLastError(); }
@@ -822,7 +822,7 @@ int bihrt_bih_blob_bytes(bihrt_ctx* c, uint64_t* bytes) {
     BihHeader h;
     int rc = fetch_header(c, &h);
     if (rc) return rc;
-    *bytes = 64 + (uint64_t)(h.quality ? (h.n > 1 ? h.n - 1 : 0) : (h.nu > 1 ? h.nu - 1 : 0)) * 16 + (uint64_t)h.n * 48;
+    *bytes = 64 + (uint64_t)(h.quality ? (h.n > 1 ? h.n - 1 : 0) : (h.nu > 1 ? h.nu - 1 : 0)) * sizeof(BihNode) + (uint64_t)h.n * 48;
     return BIHRT_OK;
 }
 
@@ -834,7 +834,7 @@ int bihrt_bih_export(bihrt_ctx* c, void* dev_dst, uint64_t bytes) {
     if (!dev_dst || bytes < need) return bihrt_fail(c, BIHRT_ERR_INVALID, "blob buffer too small (%llu < %llu)", (unsigned long long)bytes, (unsigned long long)need);
     BihHeader h;
     if ((rc = fetch_header(c, &h))) return rc;
-    const size_t nb = (size_t)(h.quality ? (h.n > 1 ? h.n - 1 : 0) : (h.nu > 1 ? h.nu - 1 : 0)) * 16, tb = (size_t)h.n * 48;
+    const size_t nb = (size_t)(h.quality ? (h.n > 1 ? h.n - 1 : 0) : (h.nu > 1 ? h.nu - 1 : 0)) * sizeof(BihNode), tb = (size_t)h.n * 48;
     uint8_t* d = (uint8_t*)dev_dst;
     BIHRT_CUDA(c, cudaMemcpyAsync(d, c->d_hdr, 64, cudaMemcpyDeviceToDevice, c->stream));
     if (nb) BIHRT_CUDA(c, cudaMemcpyAsync(d + 64, c->d_nodes, nb, cudaMemcpyDeviceToDevice, c->stream));
@@ -848,7 +848,7 @@ int bihrt_bih_import(bihrt_ctx* c, const void* dev_src, uint64_t bytes) {
     BihHeader h;
     BIHRT_CUDA(c, cudaMemcpyAsync(&h, dev_src, 64, cudaMemcpyDeviceToHost, c->stream));
     BIHRT_CUDA(c, cudaStreamSynchronize(c->stream));
-    const size_t nb = (size_t)(h.quality ? (h.n > 1 ? h.n - 1 : 0) : (h.nu > 1 ? h.nu - 1 : 0)) * 16, tb = (size_t)h.n * 48;
+    const size_t nb = (size_t)(h.quality ? (h.n > 1 ? h.n - 1 : 0) : (h.nu > 1 ? h.nu - 1 : 0)) * sizeof(BihNode), tb = (size_t)h.n * 48;
     if (h.nu > h.n || bytes < 64 + nb + tb) return bihrt_fail(c, BIHRT_ERR_INVALID, "blob truncated or corrupt");
     int rc = ensure_capacity(c, h.n, false);
     if (rc) return rc;
@@ -881,7 +881,7 @@ int bihrt_bih_region(bihrt_ctx* c, int64_t n, void** dev_ptr, uint64_t* bytes) {
         c->n = n; c->have_scene = false; c->built = false; c->topology_valid = false;
     }
     *dev_ptr = c->d_blob;
-    *bytes = 64 + (uint64_t)std::max<int64_t>(n, 1) * 16 + (uint64_t)n * 48;
+    *bytes = 64 + (uint64_t)std::max<int64_t>(n, 1) * sizeof(BihNode) + (uint64_t)n * 48;
     return BIHRT_OK;
 }
 

@@ -435,14 +435,19 @@ __global__ void __launch_bounds__(1024) k_rle_scan(uint32_t* __restrict__ tile_c
 // ------------------------------------------------------------------------------------------
 struct Box { float lo[3], hi[3]; };
 
-// heap c (0..2: max-heap of hi[c]; 3..5: min-heap of lo[c-3]) lives at heaps + c * 2P; element 1 is the
-// root, the per-slot triangle boxes sit at [P, 2P).  Entries whose subtree holds no slot below n are never
-// read by a range query inside [0, n) and are left unwritten.
+// Heap entry e (1 = root; the per-slot triangle boxes sit at [P, 2P)) = two float4 at heaps[2e], heaps[2e+1]:
+// (lo.x, lo.y, lo.z, -) and (hi.x, hi.y, hi.z, -): the six extrema of one subtree of slots in ONE 32-byte sector, so a
+// range query fetches a whole box per step.  Entries whose subtree holds no slot below n are never read by a range
+// query inside [0, n) and are left unwritten.
+__device__ __forceinline__ void heap_store(float4* __restrict__ heaps, uint32_t e, const float r[6]) {
+    heaps[2 * (size_t)e] = make_float4(r[3], r[4], r[5], 0.f);        // lo
+    heaps[2 * (size_t)e + 1] = make_float4(r[0], r[1], r[2], 0.f);    // hi
+}
 
 // One block reduces 256 consecutive elements of the level that starts at heap index `in_base` through up to 8 further
 // levels: r[] holds this thread's element on entry (3 maxima, 3 minima).  Five levels inside each warp with shuffles,
 // three more over the 8 warp results: two block barriers instead of sixteen.
-__device__ __forceinline__ void heap_reduce_block(float r[6], float (*s)[8], float* __restrict__ heaps, uint32_t P, uint32_t in_base) {
+__device__ __forceinline__ void heap_reduce_block(float r[6], float (*s)[8], float4* __restrict__ heaps, uint32_t P, uint32_t in_base) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     uint32_t level_base = in_base;
 #pragma unroll
@@ -455,10 +460,7 @@ __device__ __forceinline__ void heap_reduce_block(float r[6], float (*s)[8], flo
             r[c] = c < 3 ? fmaxf(r[c], y) : fminf(r[c], y);
         }
         const uint32_t i = (blockIdx.x * 256u + threadIdx.x) >> l;    // element of this level
-        if ((lane & ((1 << l) - 1)) == 0 && i < level_base) {
-#pragma unroll
-            for (int c = 0; c < 6; c++) heaps[(size_t)c * 2 * P + level_base + i] = r[c];
-        }
+        if ((lane & ((1 << l) - 1)) == 0 && i < level_base) heap_store(heaps, level_base + i, r);
     }
     if (lane == 0) {
 #pragma unroll
@@ -478,10 +480,7 @@ __device__ __forceinline__ void heap_reduce_block(float r[6], float (*s)[8], flo
                 r[c] = c < 3 ? fmaxf(r[c], y) : fminf(r[c], y);
             }
             const uint32_t i = (blockIdx.x * 8u + lane) >> (l - 5);
-            if (lane < 8 && (lane & ((1 << (l - 5)) - 1)) == 0 && i < level_base) {
-#pragma unroll
-                for (int c = 0; c < 6; c++) heaps[(size_t)c * 2 * P + level_base + i] = r[c];
-            }
+            if (lane < 8 && (lane & ((1 << (l - 5)) - 1)) == 0 && i < level_base) heap_store(heaps, level_base + i, r);
         }
     }
 }
@@ -492,7 +491,7 @@ __device__ __forceinline__ void heap_reduce_block(float r[6], float (*s)[8], flo
 template <bool RLE, bool QUALITY>
 __global__ void __launch_bounds__(256) k_reorder(const float* __restrict__ tri_in, const uint32_t* __restrict__ idx_sorted,
                                                  const uint32_t* __restrict__ keys_sorted, uint32_t n, BihTri* __restrict__ tris,
-                                                 float* __restrict__ heaps, uint32_t P, const uint32_t* __restrict__ tile_off,
+                                                 float4* __restrict__ heaps, uint32_t P, const uint32_t* __restrict__ tile_off,
                                                  uint32_t* __restrict__ umc, uint32_t* __restrict__ first) {
     __shared__ float s[6][8];
     __shared__ uint32_t s_w[8];
@@ -518,11 +517,8 @@ __global__ void __launch_bounds__(256) k_reorder(const float* __restrict__ tri_i
         minmax3(v[0], v[3], v[6], mn[0], mx[0]);
         minmax3(v[1], v[4], v[7], mn[1], mx[1]);
         minmax3(v[2], v[5], v[8], mn[2], mx[2]);
-#pragma unroll
-        for (int a = 0; a < 3; a++) {
-            heaps[(size_t)a * 2 * P + P + j] = mx[a];
-            heaps[(size_t)(3 + a) * 2 * P + P + j] = mn[a];
-        }
+        const float r0[6] = { mx[0], mx[1], mx[2], mn[0], mn[1], mn[2] };
+        heap_store(heaps, P + j, r0);
     }
     if (RLE) {
         // run-length encoding of the sorted keys (thrust::reduce_by_key + unique_by_key_copy, R/src/Renderer.cpp:450-472):
@@ -536,30 +532,46 @@ __global__ void __launch_bounds__(256) k_reorder(const float* __restrict__ tri_i
 }
 
 // 8 more levels above the level of `in_count` used elements that starts at heap index `in_base`
-__global__ void __launch_bounds__(256) k_heap_up(float* __restrict__ heaps, uint32_t P, uint32_t in_base, uint32_t in_count) {
+__global__ void __launch_bounds__(256) k_heap_up(float4* __restrict__ heaps, uint32_t P, uint32_t in_base, uint32_t in_count) {
     __shared__ float s[6][8];
     const uint32_t i = blockIdx.x * 256u + threadIdx.x;
-    float r[6];
-#pragma unroll
-    for (int c = 0; c < 6; c++)
-        r[c] = i < in_count ? heaps[(size_t)c * 2 * P + in_base + i] : (c < 3 ? -INFINITY : INFINITY);
+    float r[6] = { -INFINITY, -INFINITY, -INFINITY, INFINITY, INFINITY, INFINITY };
+    if (i < in_count) {
+        const float4 lo = heaps[2 * (size_t)(in_base + i)], hi = heaps[2 * (size_t)(in_base + i) + 1];
+        r[0] = hi.x; r[1] = hi.y; r[2] = hi.z; r[3] = lo.x; r[4] = lo.y; r[5] = lo.z;
+    }
     heap_reduce_block(r, s, heaps, P, in_base);
 }
 
-template <bool IS_MAX>
-__device__ __forceinline__ float heap_range(const float* __restrict__ h, uint32_t P, uint32_t l, uint32_t r /* inclusive */) {
-    float res = IS_MAX ? -INFINITY : INFINITY;
-    l += P; r += P + 1;
-    while (l < r) {
-        if (l & 1u) { const float x = __ldg(h + l); res = IS_MAX ? fmaxf(res, x) : fminf(res, x); l++; }
-        if (r & 1u) { r--; const float x = __ldg(h + r); res = IS_MAX ? fmaxf(res, x) : fminf(res, x); }
-        l >>= 1; r >>= 1;
+// Boxes of the slot ranges [l0, r0) and [l1, r1) (heap indices at the bottom level), both walked in one loop so that up to
+// eight independent 128-bit loads are in flight; box = lo.xyz, hi.xyz.
+__device__ __forceinline__ void heap_merge(const float4* __restrict__ heaps, uint32_t e, float b[6]) {
+    const float4 lo = __ldg(heaps + 2 * (size_t)e), hi = __ldg(heaps + 2 * (size_t)e + 1);
+    b[0] = fminf(b[0], lo.x); b[1] = fminf(b[1], lo.y); b[2] = fminf(b[2], lo.z);
+    b[3] = fmaxf(b[3], hi.x); b[4] = fmaxf(b[4], hi.y); b[5] = fmaxf(b[5], hi.z);
+}
+__device__ __forceinline__ void heap_range_boxes(const float4* __restrict__ heaps, uint32_t l0, uint32_t r0, uint32_t l1, uint32_t r1,
+                                                 float bl[6], float br[6]) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) { bl[k] = br[k] = INFINITY; bl[3 + k] = br[3 + k] = -INFINITY; }
+    while (l0 < r0 || l1 < r1) {
+        if (l0 < r0) { if (l0 & 1u) heap_merge(heaps, l0++, bl); if (r0 & 1u) heap_merge(heaps, --r0, bl); l0 >>= 1; r0 >>= 1; }
+        if (l1 < r1) { if (l1 & 1u) heap_merge(heaps, l1++, br); if (r1 & 1u) heap_merge(heaps, --r1, br); l1 >>= 1; r1 >>= 1; }
     }
-    return res;
+}
+__device__ __forceinline__ void node_store(BihNode* __restrict__ nd, int axis, uint32_t ref_l, uint32_t ref_r, const float bl[6], const float br[6]) {
+    float4* p = reinterpret_cast<float4*>(nd);
+    // clip planes = the children's extents on the split axis: max of hi[axis] over the left subtree, min of lo[axis] over the
+    // right one -- the same maxima / minima of the same input floats as the reference's float atomics (:52-66,532-547)
+    const float c0 = axis == 0 ? bl[3] : (axis == 1 ? bl[4] : bl[5]), c1 = axis == 0 ? br[0] : (axis == 1 ? br[1] : br[2]);
+    p[0] = make_float4(c0, c1, __uint_as_float(ref_l), __uint_as_float(ref_r));
+    p[1] = make_float4(bl[0], bl[1], bl[2], bl[3]);
+    p[2] = make_float4(bl[4], bl[5], br[0], br[1]);
+    p[3] = make_float4(br[2], br[3], br[4], br[5]);
 }
 
 __global__ void __launch_bounds__(128) k_nodes(const uint32_t* __restrict__ umc, const uint32_t* __restrict__ first,
-                                               BihHeader* hdr, const float* __restrict__ heaps, uint32_t P,
+                                               BihHeader* hdr, const float4* __restrict__ heaps, uint32_t P,
                                                BihNode* __restrict__ nodes, uint32_t* __restrict__ status_map) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int nu = (int)hdr->nu;
@@ -595,19 +607,9 @@ __global__ void __launch_bounds__(128) k_nodes(const uint32_t* __restrict__ umc,
                                             : BIH_REF_NODE(split + 1, (__clz(ms1 ^ __ldg(umc + b)) + 1) % 3);
     // leaves [a, split] are slots [first[a], first[split+1]); leaves [split+1, b] are [first[split+1], first[b+1])
     const uint32_t sa = __ldg(first + a), sm = __ldg(first + split + 1), sb = __ldg(first + b + 1);
-    // both range queries walk their heaps in one loop so that up to four independent loads are in flight
-    const float* hmax = heaps + (size_t)axis * 2 * P;
-    const float* hmin = heaps + (size_t)(3 + axis) * 2 * P;
-    float cl0 = -INFINITY, cl1 = INFINITY;
-    uint32_t l0 = sa + P, r0 = sm + P, l1 = sm + P, r1 = sb + P;          // half-open [l, r) at the leaf level
-    while (l0 < r0 || l1 < r1) {
-        float a0 = -INFINITY, b0 = -INFINITY, a1 = INFINITY, b1 = INFINITY;
-        if (l0 < r0) { if (l0 & 1u) a0 = __ldg(hmax + l0++); if (r0 & 1u) b0 = __ldg(hmax + --r0); l0 >>= 1; r0 >>= 1; }
-        if (l1 < r1) { if (l1 & 1u) a1 = __ldg(hmin + l1++); if (r1 & 1u) b1 = __ldg(hmin + --r1); l1 >>= 1; r1 >>= 1; }
-        cl0 = fmaxf(cl0, fmaxf(a0, b0));
-        cl1 = fminf(cl1, fminf(a1, b1));
-    }
-    *reinterpret_cast<float4*>(nodes + idx) = make_float4(cl0, cl1, __uint_as_float(ref_l), __uint_as_float(ref_r));
+    float bl[6], br[6];
+    heap_range_boxes(heaps, sa + P, sm + P, sm + P, sb + P, bl, br);
+    node_store(nodes + idx, axis, ref_l, ref_r, bl, br);
     if (idx == 0) hdr->root_axis = (uint32_t)axis;
 }
 
@@ -679,7 +681,7 @@ __device__ __forceinline__ int delta_q(const uint64_t* __restrict__ keys, int n,
 __device__ __forceinline__ uint32_t axis_of_prefix(int p) { return (uint32_t)((p + 2) % 3); }
 
 __global__ void __launch_bounds__(128) k_nodes_q(const uint64_t* __restrict__ keys, uint32_t n_, uint32_t cap, BihHeader* hdr,
-                                                 const float* __restrict__ heaps, uint32_t P, BihNode* __restrict__ nodes,
+                                                 const float4* __restrict__ heaps, uint32_t P, BihNode* __restrict__ nodes,
                                                  BihTri* __restrict__ tris, uint32_t* __restrict__ status_map) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int n = (int)n_;
@@ -719,18 +721,9 @@ __global__ void __launch_bounds__(128) k_nodes_q(const uint64_t* __restrict__ ke
             const uint32_t ref_r = leaf_r ? BIH_REF_LEAFREF(split + 1) : BIH_REF_NODE(split + 1, axis_of_prefix(pre(ks1, kb, split + 1, b)));
             if (leaf_l) { tris[split].last = 1u; made++; }
             if (leaf_r) { tris[b].last = 1u; made++; }
-            const float* hmax = heaps + (size_t)axis * 2 * P;
-            const float* hmin = heaps + (size_t)(3 + axis) * 2 * P;
-            float cl0 = -INFINITY, cl1 = INFINITY;
-            uint32_t l0 = a + P, r0 = split + 1 + P, l1 = split + 1 + P, r1 = b + 1 + P;
-            while (l0 < r0 || l1 < r1) {
-                float a0 = -INFINITY, b0 = -INFINITY, a1 = INFINITY, b1 = INFINITY;
-                if (l0 < r0) { if (l0 & 1u) a0 = __ldg(hmax + l0++); if (r0 & 1u) b0 = __ldg(hmax + --r0); l0 >>= 1; r0 >>= 1; }
-                if (l1 < r1) { if (l1 & 1u) a1 = __ldg(hmin + l1++); if (r1 & 1u) b1 = __ldg(hmin + --r1); l1 >>= 1; r1 >>= 1; }
-                cl0 = fmaxf(cl0, fmaxf(a0, b0));
-                cl1 = fminf(cl1, fminf(a1, b1));
-            }
-            *reinterpret_cast<float4*>(nodes + idx) = make_float4(cl0, cl1, __uint_as_float(ref_l), __uint_as_float(ref_r));
+            float bl[6], br[6];
+            heap_range_boxes(heaps, a + P, split + 1 + P, split + 1 + P, b + 1 + P, bl, br);
+            node_store(nodes + idx, (int)axis, ref_l, ref_r, bl, br);
             if (idx == 0) hdr->root_axis = axis;
         }
     }

@@ -115,10 +115,13 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
     constexpr int STACK_DEPTH = Q ? STACK_DEPTH_QUALITY : STACK_DEPTH_PARITY;
     // per-axis ray constants (origin, 1/dir), one row of 3 float2 per thread: 24-byte stride keeps a
     // half-warp's 64-bit accesses on distinct banks when the lanes agree on the axis
-    __shared__ float2 s_ray[TRACE_THREADS * 3];
+    // per-thread ray record in shared memory, 10 words: (ox, 1/dx) (oy, 1/dy) (oz, 1/dz) dx dy dz -.  The node step picks
+    // (origin, 1/dir) of the node's axis with one 64-bit LDS (40-byte stride: a half-warp's accesses fall on distinct banks
+    // when the lanes agree on the axis); the direction is only needed by the triangle test, so it lives here, not in registers.
+    __shared__ __align__(16) float s_ray[TRACE_THREADS * 10];
     const int lane = threadIdx.x & 31;
     const uint32_t lt = (1u << lane) - 1u;
-    float2* my_ray = s_ray + threadIdx.x * 3;
+    float* my_ray = s_ray + threadIdx.x * 10;
     const char* __restrict__ nodes_b = reinterpret_cast<const char*>(a.nodes);
     const char* __restrict__ tris_b = reinterpret_cast<const char*>(a.tris);
     const BihTri* __restrict__ tris = a.tris;
@@ -158,7 +161,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
     uint64_t item = ~0ull;                     // current work item, ~0 = none
     int s = 0, s0 = 0;                         // sample of the item being traced, first sample of the item
     uint32_t hits = 0, pixel = 0, pxy = 0;
-    float ox = 0.f, oy = 0.f, oz = 0.f, dx = 1.f, dy = 1.f, dz = 1.f;
+    float ox = 0.f, oy = 0.f, oz = 0.f, ix = 1.f, iy = 1.f, iz = 1.f;      // origin and 1/direction (the boxes need all three axes)
     uint32_t cur = NONE;                       // item being walked: node index, leaf|slot, or NONE
     float rMin = 0.f, pMin = 0.f, pMax = 0.f;
     Hit h; h.t = FLT_MAX; h.slot = -1;
@@ -339,6 +342,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
             }
             // start the next ray of every idle lane that owns an item
             if (cur == NONE && item != ~0ull) {
+                float dx, dy, dz;
                 if (MODE == 0) {
                     const float* p = reinterpret_cast<const float*>(a.rays + item);
                     ox = __ldg(p); oy = __ldg(p + 1); oz = __ldg(p + 2); dx = __ldg(p + 3); dy = __ldg(p + 4); dz = __ldg(p + 5);
@@ -355,7 +359,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
                     dz = __fsub_rn(__fadd_rn(__fadd_rn(a.cam.lower_left[2], __fmul_rn(uu, a.cam.horizontal[2])), __fmul_rn(vv, a.cam.vertical[2])), oz);
                 }
                 // Ray::Ray, R/src/Ray.cu:3-10
-                const float ix = __frcp_rn(dx), iy = __frcp_rn(dy), iz = __frcp_rn(dz);
+                ix = __frcp_rn(dx); iy = __frcp_rn(dy); iz = __frcp_rn(dz);
                 if (MODE == 0 && fresh) {
                     // ray lists: a packet whose directions disagree in sign is incoherent (diffuse bounces);
                     // there, lanes that finish early are worth refilling before the whole packet has drained
@@ -365,7 +369,9 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
                     const bool mixed = ((bx != 0 && bx != m) + (by != 0 && by != m) + (bz != 0 && bz != m)) >= 2;
                     new_thresh = mixed ? min(a.refill_threshold, a.refill_incoherent) : a.refill_threshold;
                 }
-                my_ray[0] = make_float2(ox, ix); my_ray[1] = make_float2(oy, iy); my_ray[2] = make_float2(oz, iz);
+                *reinterpret_cast<float2*>(my_ray) = make_float2(ox, ix); *reinterpret_cast<float2*>(my_ray + 2) = make_float2(oy, iy);
+                *reinterpret_cast<float2*>(my_ray + 4) = make_float2(oz, iz); *reinterpret_cast<float2*>(my_ray + 6) = make_float2(dx, dy);
+                my_ray[8] = dz;
                 // occlusion queries (MODE 0, any_hit): only hits before tmax count, and the first one found ends the ray
                 h.t = (MODE == 0 && a.any_hit) ? a.tmax : FLT_MAX; h.slot = -1; STACK_RESET(); tracing = true;
                 // slab test against the scene box, R/src/CUDAKernels.cu:237-262 (same operation order)
@@ -408,6 +414,17 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
         // come off the stack -- h.t may have shrunk since they were pushed -- are checked (POP_VALID); an
         // item that fails is dropped without a node fetch.  Same visits, same order, same counters as the
         // entry check of oracle/bih_oracle.c:traverse_proper.
+#define BOX_EPS 2.384185791015625e-07f      /* 2^-22 */
+#define BOX_SLAB(lx, ly, lz, hx, hy, hz, bn, bf)                                                            \
+        do {                                                                                                \
+            const float ax0 = __fmul_rn(__fsub_rn((lx), ox), ix), ax1 = __fmul_rn(__fsub_rn((hx), ox), ix); \
+            const float ay0 = __fmul_rn(__fsub_rn((ly), oy), iy), ay1 = __fmul_rn(__fsub_rn((hy), oy), iy); \
+            const float az0 = __fmul_rn(__fsub_rn((lz), oz), iz), az1 = __fmul_rn(__fsub_rn((hz), oz), iz); \
+            const float n_ = fmaxf(fmaxf(fminf(ax0, ax1), fminf(ay0, ay1)), fminf(az0, az1));               \
+            const float f_ = fminf(fminf(fmaxf(ax0, ax1), fmaxf(ay0, ay1)), fmaxf(az0, az1));               \
+            (bn) = __fmaf_rn(-fabsf(n_), BOX_EPS, n_);                                                      \
+            (bf) = __fmaf_rn(fabsf(f_), BOX_EPS, f_);                                                       \
+        } while (0)
 #define POP_VALID()                                                                                         \
         do {                                                                                                \
             cur = NONE;                                                                                     \
@@ -426,10 +443,10 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
                 uint32_t ra;
                 asm("mad.lo.u32 %0, %1, 8, %2;" : "=r"(ra) : "r"(cur & 3u), "r"(ray_smem));
                 asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(oi.x), "=f"(oi.y) : "r"(ra));
-                // node address = base + index * 16, as one 32x32->64 multiply-add on the base pointer
+                // node address = base + index * 64, as one 32x32->64 multiply-add on the base pointer
                 const float4* np;
-                asm("mad.wide.u32 %0, %1, 16, %2;" : "=l"(np) : "r"(cur >> 2), "l"(nodes_b));
-                const float4 nd = __ldg(np);
+                asm("mad.wide.u32 %0, %1, 64, %2;" : "=l"(np) : "r"(cur >> 2), "l"(nodes_b));
+                const float4 nd = __ldg(np), b0 = __ldg(np + 1), b1 = __ldg(np + 2), b2 = __ldg(np + 3);
                 if (COUNTED) { nnodes++; const uint32_t am = __activemask(); wnode += (lane == __ffs(am) - 1); }
                 const uint32_t rl = __float_as_uint(nd.z), rr = __float_as_uint(nd.w);
                 const bool neg = oi.y < 0.f;                           // near = sign[axis], :286
@@ -439,16 +456,25 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
                 const uint32_t refn = neg ? rr : rl, reff = neg ? rl : rr;
                 const float nMax = fminf(pMax, tn);
                 const float fMin = fmaxf(pMin, tf);
-                const bool go_near = (Q || rMin < tn) && (pMin <= nMax);   // reference's strict test (:292) + closed tight interval
-                const bool go_far = (fMin <= pMax);
+                // the children's boxes: parametric interval of the ray inside each (slab test on all three axes; min / max of
+                // the two plane distances per axis orders them whatever the sign of the direction, and drops the NaN of a
+                // zero direction component on a box face), widened by 2^-22 relative so that rounding never culls a box the
+                // exact ray touches.  A child the ray misses is never fetched; a child that is entered gets the tighter interval.
+                float bnL, bfL, bnR, bfR;
+                BOX_SLAB(b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, bnL, bfL);
+                BOX_SLAB(b1.z, b1.w, b2.x, b2.y, b2.z, b2.w, bnR, bfR);
+                const float nLo = fmaxf(pMin, neg ? bnR : bnL), nHi = fminf(nMax, neg ? bfR : bfL);
+                const float fLo = fmaxf(fMin, neg ? bnL : bnR), fHi = fminf(pMax, neg ? bfL : bfR);
+                const bool go_near = (Q || rMin < tn) && (nLo <= nHi);   // reference's strict test (:292) + closed tight interval
+                const bool go_far = (fLo <= fHi);
                 if (go_near && go_far) {
                     // near before far, except a far LEAF next to a near NODE is tested first (:344-349)
                     if ((int)refn >= 0 && (int)reff < 0) {
-                        STACK_PUSH(make_uint4(refn, __float_as_uint(rMin), __float_as_uint(pMin), __float_as_uint(nMax)));
-                        cur = reff; rMin = tf; pMin = fMin;
+                        STACK_PUSH(make_uint4(refn, __float_as_uint(rMin), __float_as_uint(nLo), __float_as_uint(nHi)));
+                        cur = reff; rMin = tf; pMin = fLo; pMax = fHi;
                     } else {
-                        STACK_PUSH(make_uint4(reff, __float_as_uint(tf), __float_as_uint(fMin), __float_as_uint(pMax)));
-                        cur = refn; pMax = nMax;
+                        STACK_PUSH(make_uint4(reff, __float_as_uint(tf), __float_as_uint(fLo), __float_as_uint(fHi)));
+                        cur = refn; pMin = nLo; pMax = nHi;
                     }
                     // depth: a root-to-leaf path pushes at most one item per Morton bit, so sp <= 30 < STACK_DEPTH by
                     // construction; the instrumented build reports the deepest stack (counters[2]) and refuses to run past
@@ -457,8 +483,8 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
 #ifdef BIHRT_DEBUG_STACK
                     if (sp >= STACK_DEPTH) __trap();
 #endif
-                } else if (go_near) { cur = refn; pMax = nMax; }
-                else if (go_far) { cur = reff; rMin = tf; pMin = fMin; }
+                } else if (go_near) { cur = refn; pMin = nLo; pMax = nHi; }
+                else if (go_far) { cur = reff; rMin = tf; pMin = fLo; pMax = fHi; }
                 else POP_VALID();
             }
             const uint32_t m_walk = __ballot_sync(FULL, (int)cur >= 0);
@@ -472,11 +498,13 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
         if (cur + 1u > 0x80000000u) {
             const char* tp;
             asm("mad.wide.u32 %0, %1, 12, %2;" : "=l"(tp) : "r"(cur & 0x7FFFFFFCu), "l"(tris_b));
-            test_leaf<COUNTED>(tp, ox, oy, oz, dx, dy, dz, h, ntris, wleaf);
+            const float2 dxy = *reinterpret_cast<const float2*>(my_ray + 6);
+            test_leaf<COUNTED>(tp, ox, oy, oz, dxy.x, dxy.y, my_ray[8], h, ntris, wleaf);
             if (MODE == 0 && a.any_hit && h.slot >= 0) { STACK_RESET(); cur = NONE; }      // occluded: nothing else to learn
             else POP_VALID();
         }
 #undef POP_VALID
+#undef BOX_SLAB
 #undef STACK_RESET
 #undef STACK_PUSH
 #undef STACK_POP

@@ -116,7 +116,14 @@ BIHRT_API const char* bihrt_last_error(const bihrt_ctx* ctx);                   
 BIHRT_API int         bihrt_set_stream(bihrt_ctx* ctx, void* cuda_stream);
 BIHRT_API int         bihrt_get_stream(bihrt_ctx* ctx, void** cuda_stream);     /* the cudaStream_t the context launches on */
 BIHRT_API int         bihrt_sync(bihrt_ctx* ctx);                               /* replaces the cudaDeviceSynchronize after each step, R/src/Renderer.cpp:428-503 */
-BIHRT_API int         bihrt_set_option(bihrt_ctx* ctx, const char* name, int64_t value);  /* tuning knobs, see DESIGN.md */
+/* Options (DESIGN.md has the full list of tuning knobs).  The two that change WHAT is built:
+ *   "morton_bits" 30 (default): the reference's 10-bit grid per axis, R/src/Renderer.cpp:116-136 -- the parity path, bit-exact tree.
+ *                 63: QUALITY MODE, not a parity path: 21 bits per axis, ties broken by sorted position,
+ *                 every subtree of at most "leaf_cap" (default 4, 1..64) triangles collapsed into one leaf.  Hits equal brute force
+ *                 (including on axis-aligned geometry where the reference's strict comparisons lose hits); bihrt_refit and
+ *                 bihrt_export_reference_view are not available.  A context that adopts a replicated BIH (bihrt_bih_adopt) must
+ *                 have the builder's value; bihrt_bih_copy and bihrt_bih_import carry it over themselves. */
+BIHRT_API int         bihrt_set_option(bihrt_ctx* ctx, const char* name, int64_t value);
 BIHRT_API int         bihrt_get_stat(bihrt_ctx* ctx, const char* name, int64_t* value);   /* "kernel_launches": kernels of this library launched so far */
 
 /* ---- scene load: App::LoadModels + GPUArrayManager::Allocate*, R/src/App.cpp:65-167,

@@ -506,6 +506,121 @@ static void traverse_proper(const orc_scene* s, const orc_ray* r, orc_hit* rec, 
     }
 }
 
+/* mode 3 -- what the shipped kernel does (csrc/trace.cu): traverse_proper plus the BOUNDING BOXES OF THE TWO CHILDREN,
+ * which the B200 node record carries next to the reference's two clip planes (csrc/bihrt_internal.cuh:BihNode).  A child
+ * whose box the ray misses inside the child's interval is not entered, and an entered child's interval is cut to the
+ * box.  The boxes are exact min / max of vertex coordinates, so the leaves entered are a SUBSET of traverse_proper's, in
+ * the same order: a leaf is skipped only when the ray cannot hit a triangle in it before the closest hit so far -- the
+ * result equals traverse_proper's (and hence TraverseTree's) except where Moller-Trumbore's rounded t disagrees with a
+ * rounded box distance by more than the 2^-22 relative margin, i.e. on grazing edge / vertex hits (the documented tie
+ * class).  Same arithmetic, operation order and NaN behaviour as the kernel, so GPU results and counters are compared
+ * bit for bit against this mode; tests/test_oracle_semantics.py ties it back to traverse_ref. */
+#define BOX_EPS 2.384185791015625e-07f      /* 2^-22 */
+static inline void box_slab(const float* b /* lo.xyz hi.xyz */, const orc_ray* r, float* bn, float* bf) {
+    float ax0 = (b[0] - r->o[0]) * r->inv[0], ax1 = (b[3] - r->o[0]) * r->inv[0];
+    float ay0 = (b[1] - r->o[1]) * r->inv[1], ay1 = (b[4] - r->o[1]) * r->inv[1];
+    float az0 = (b[2] - r->o[2]) * r->inv[2], az1 = (b[5] - r->o[2]) * r->inv[2];
+    float n_ = dev_fmaxf(dev_fmaxf(dev_fminf(ax0, ax1), dev_fminf(ay0, ay1)), dev_fminf(az0, az1));
+    float f_ = dev_fminf(dev_fminf(dev_fmaxf(ax0, ax1), dev_fmaxf(ay0, ay1)), dev_fmaxf(az0, az1));
+    *bn = fmaf(-fabsf(n_), BOX_EPS, n_);
+    *bf = fmaf(fabsf(f_), BOX_EPS, f_);
+}
+
+static void traverse_box(const orc_scene* s, const float* cbox /* 12 floats per node: left box, right box */,
+                         const orc_ray* r, orc_hit* rec, orc_counters* c) {
+    float rMin, sMax;
+    if (s->nu <= 0) return;
+    if (!scene_slab(s, r, &rMin, &sMax)) return;
+    if (s->nu == 1) { find_nearest(s, r, 0, rec, c); return; }
+    float pMin = dev_fmaxf(rMin, 0.0f), pMax = sMax;
+    struct { int ref; float rMin, pMin, pMax; } stack[64];
+    int sp = 0;
+    int cur = 0;
+    for (;;) {
+        int next = 0;
+        if (pMin <= dev_fminf(pMax, (float)rec->t)) {
+            pMax = dev_fminf(pMax, (float)rec->t);
+            if (cur < 0) {
+                find_nearest(s, r, ~cur, rec, c);
+            } else {
+                c->nodes++;
+                int ax = s->axis[cur];
+                float org = r->o[ax], inv = r->inv[ax];
+                int near = r->sign[ax], far = 1 - near;
+                float t0 = (s->clip[2 * cur] - org) * inv;
+                float t1 = (s->clip[2 * cur + 1] - org) * inv;
+                float tn = near ? t1 : t0, tf = near ? t0 : t1;
+                const uint8_t* lf = s->is_leaf + 2 * cur;
+                const int32_t* ch = s->children + 2 * cur;
+                int refn = lf[near] ? ~ch[near] : ch[near], reff = lf[far] ? ~ch[far] : ch[far];
+                float nMax = dev_fminf(pMax, tn);
+                float fMin = dev_fmaxf(pMin, tf);
+                float bn[2], bf[2];
+                box_slab(cbox + 12 * (int64_t)cur, r, &bn[0], &bf[0]);
+                box_slab(cbox + 12 * (int64_t)cur + 6, r, &bn[1], &bf[1]);
+                float nLo = dev_fmaxf(pMin, bn[near]), nHi = dev_fminf(nMax, bf[near]);
+                float fLo = dev_fmaxf(fMin, bn[far]), fHi = dev_fminf(pMax, bf[far]);
+                int go_near = (rMin < tn) && (nLo <= nHi);
+                int go_far = (fLo <= fHi);
+                if (go_near && go_far) {
+                    if (refn >= 0 && reff < 0) {
+                        stack[sp].ref = refn; stack[sp].rMin = rMin; stack[sp].pMin = nLo; stack[sp].pMax = nHi;
+                        cur = reff; rMin = tf; pMin = fLo; pMax = fHi;
+                    } else {
+                        stack[sp].ref = reff; stack[sp].rMin = tf; stack[sp].pMin = fLo; stack[sp].pMax = fHi;
+                        cur = refn; pMin = nLo; pMax = nHi;
+                    }
+                    sp++;
+                    if (sp > c->max_stack) c->max_stack = sp;
+                    next = 1;
+                } else if (go_near) { cur = refn; pMin = nLo; pMax = nHi; next = 1; }
+                else if (go_far) { cur = reff; rMin = tf; pMin = fLo; pMax = fHi; next = 1; }
+            }
+        }
+        if (next) continue;
+        if (sp == 0) break;
+        sp--;
+        cur = stack[sp].ref; rMin = stack[sp].rMin; pMin = stack[sp].pMin; pMax = stack[sp].pMax;
+    }
+}
+
+/* children boxes of every internal node: exact min / max over the vertices below each child (what the GPU build derives
+ * from its min / max heaps, csrc/build.cu:k_nodes).  cbox: 12 floats per node. */
+static void children_boxes(const orc_scene* s, float* cbox) {
+    int64_t nu = s->nu, ni = nu > 1 ? nu - 1 : 0;
+    float* lbox = (float*)malloc(sizeof(float) * 6 * (size_t)(nu > 0 ? nu : 1));
+    float* nbox = (float*)malloc(sizeof(float) * 6 * (size_t)(ni > 0 ? ni : 1));
+    char* done = (char*)calloc((size_t)(ni > 0 ? ni : 1), 1);
+    for (int64_t l = 0; l < nu; l++) {
+        float* b = lbox + 6 * l;
+        for (int k = 0; k < 3; k++) { b[k] = INFINITY; b[3 + k] = -INFINITY; }
+        for (uint32_t j = 0; j < s->cnt[l]; j++) {
+            const float* t = s->tri9 + 9 * (int64_t)s->tris_idx[s->first[l] + j];
+            for (int v = 0; v < 3; v++) for (int k = 0; k < 3; k++) {
+                b[k] = dev_fminf(b[k], t[3 * v + k]); b[3 + k] = dev_fmaxf(b[3 + k], t[3 * v + k]);
+            }
+        }
+    }
+    /* children have arbitrary indices (Karras numbering): sweep until every node has both children's boxes */
+    int64_t remaining = ni;
+    while (remaining > 0)
+        for (int64_t i = 0; i < ni; i++) if (!done[i]) {
+            const float* cb[2]; int ok = 1;
+            for (int k = 0; k < 2; k++) {
+                int chd = s->children[2 * i + k];
+                if (s->is_leaf[2 * i + k]) cb[k] = lbox + 6 * (int64_t)chd;
+                else if (done[chd]) cb[k] = nbox + 6 * (int64_t)chd;
+                else ok = 0;
+            }
+            if (!ok) continue;
+            float* b = nbox + 6 * i;
+            for (int k = 0; k < 3; k++) { b[k] = dev_fminf(cb[0][k], cb[1][k]); b[3 + k] = dev_fmaxf(cb[0][3 + k], cb[1][3 + k]); }
+            memcpy(cbox + 12 * i, cb[0], 24); memcpy(cbox + 12 * i + 6, cb[1], 24);
+            done[i] = 1; remaining--;
+        }
+    free(done); free(nbox); free(lbox);
+}
+
 /* brute force over every slot in slot order (the reference's commented-out TraverseTriangles,
  * R/src/CUDAKernels.cu:157-202, visits leaves in node order instead; same result except exact ties) */
 static void traverse_brute(const orc_scene* s, const orc_ray* r, orc_hit* rec, orc_counters* c) {
@@ -517,7 +632,7 @@ static void traverse_brute(const orc_scene* s, const orc_ray* r, orc_hit* rec, o
     }
 }
 
-/* mode: 0 = reference semantics, 1 = proper traversal, 2 = brute force.
+/* mode: 0 = reference semantics, 1 = proper traversal, 2 = brute force, 3 = proper traversal + children boxes (the shipped kernel).
  * rays6: o.xyz d.xyz per ray.  Outputs: t (FLT_MAX on miss), slot (-1), prim = tris_idx[slot] (-1).
  * counters3 (may be NULL): total nodes visited, total triangle tests, max stack depth. */
 ORC_API void orc_trace(int mode, const float* tri9, int64_t n, int64_t nu,
@@ -529,6 +644,8 @@ ORC_API void orc_trace(int mode, const float* tri9, int64_t n, int64_t nu,
     orc_scene s = { tri9, n, nu, tris_idx, cnt, first, clip, axis, is_leaf, children, {0, 0, 0}, {0, 0, 0} };
     for (int k = 0; k < 3; k++) { s.scene_lo[k] = scene_lo[k]; s.scene_hi[k] = scene_hi[k]; }
     uint64_t tot_nodes = 0, tot_tris = 0; int max_stack = 0;
+    float* cbox = NULL;
+    if (mode == 3) { cbox = (float*)malloc(sizeof(float) * 12 * (size_t)(nu > 1 ? nu - 1 : 1)); children_boxes(&s, cbox); }
 #ifdef _OPENMP
     if (nthreads <= 0) nthreads = omp_get_max_threads();
 #pragma omp parallel for schedule(dynamic, 256) num_threads(nthreads) reduction(+:tot_nodes, tot_tris) reduction(max:max_stack)
@@ -540,6 +657,7 @@ ORC_API void orc_trace(int mode, const float* tri9, int64_t n, int64_t nu,
         orc_counters c = { 0, 0, 0 };
         if (mode == 0) traverse_ref(&s, &r, &rec, &c);
         else if (mode == 1) traverse_proper(&s, &r, &rec, &c);
+        else if (mode == 3) traverse_box(&s, cbox, &r, &rec, &c);
         else traverse_brute(&s, &r, &rec, &c);
         out_t[i] = (float)rec.t;
         out_slot[i] = rec.slot;
@@ -547,6 +665,7 @@ ORC_API void orc_trace(int mode, const float* tri9, int64_t n, int64_t nu,
         tot_nodes += c.nodes; tot_tris += c.tris;
         if (c.max_stack > max_stack) max_stack = c.max_stack;
     }
+    free(cbox);
     if (counters3) { counters3[0] = tot_nodes; counters3[1] = tot_tris; counters3[2] = (uint64_t)max_stack; }
 }
 

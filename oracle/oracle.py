@@ -74,7 +74,8 @@ class Bih:
         self.children, self.parent = self.children[:ni], self.parent[:ni]
 
     def trace(self, rays6, mode="ref", threads=0, want_counters=False):
-        """mode: 'ref' (literal TraverseTree), 'proper', 'brute'.  Returns t, slot, prim[, counters]."""
+        """mode: 'ref' (literal TraverseTree), 'proper' (pruned, same results), 'box' (proper + children boxes: what the
+        shipped kernel does, bit for bit), 'brute'.  Returns t, slot, prim[, counters]."""
         rays6 = np.ascontiguousarray(rays6, dtype=np.float32).reshape(-1, 6)
         nr = rays6.shape[0]
         t = np.empty(nr, np.float32)
@@ -83,7 +84,7 @@ class Bih:
         counters = np.zeros(3, np.uint64)
         keep = [np.ascontiguousarray(x) for x in (self.tris_idx, self.cnt, self.first, self.clip,
                                                  self.axis, self.is_leaf, self.children)]
-        lib().orc_trace(C.c_int({"ref": 0, "proper": 1, "brute": 2}[mode]), _p(self.tri9),
+        lib().orc_trace(C.c_int({"ref": 0, "proper": 1, "brute": 2, "box": 3}[mode]), _p(self.tri9),
                         C.c_int64(self.n), C.c_int64(self.nu), *[_p(k) for k in keep],
                         _p(self.scene_lo), _p(self.scene_hi), _p(rays6), C.c_int64(nr), _p(t),
                         _p(slot), _p(prim), _p(counters), C.c_int(threads))

@@ -27,6 +27,12 @@ def test_pruned_traversal_equals_reference_traversal(oracle, scenes, name):
     np.testing.assert_array_equal(p0, p1)
     assert c1["nodes"] <= c0["nodes"] and c1["tris"] <= c0["tris"]
     assert c1["max_stack"] <= 30
+    # ... and the shipped traversal (children boxes next to the clip planes) enters a subset of those leaves: same result
+    t3, s3, p3, c3 = b.trace(rays, "box", want_counters=True)
+    np.testing.assert_array_equal(s0, s3)
+    np.testing.assert_array_equal(t0, t3)
+    np.testing.assert_array_equal(p0, p3)
+    assert c3["nodes"] <= c1["nodes"] and c3["tris"] <= c1["tris"] and c3["max_stack"] <= c1["max_stack"]
 
 
 @pytest.mark.parametrize("name", ["dodecahedron", "sphere16", "soup"])
@@ -51,7 +57,10 @@ def test_flat_geometry_boundary_is_reference_behaviour(oracle, scenes):
     t0, s0, _ = b.trace(rays, "ref")
     t1, s1, _ = b.trace(rays, "proper")
     t2, s2, _ = b.trace(rays, "brute")
+    t3, s3, _ = b.trace(rays, "box")
     np.testing.assert_array_equal(s0, s1)
+    np.testing.assert_array_equal(s0, s3)
+    np.testing.assert_array_equal(t0, t3)
     assert (t0 != t2).sum() > 0           # the reference is not brute force here
     assert np.all(t0 >= t2)               # it can only miss closer hits, never invent one
 
