@@ -137,7 +137,7 @@ void bihrt_destroy(bihrt_ctx* c) {
     dev_free(&c->d_umc); dev_free(&c->d_first); dev_free(&c->d_hist); dev_free(&c->d_lookback);
     dev_free(&c->d_heaps); dev_free(&c->d_scenebox_enc);
     dev_free(&c->d_keys64[0]); dev_free(&c->d_keys64[1]); dev_free(&c->d_lookback_q);
-    dev_free(&c->d_fb); dev_free(&c->d_counters); dev_free(&c->d_work);
+    dev_free(&c->d_fb); dev_free(&c->d_counters); dev_free(&c->d_work); dev_free(&c->d_top);
     for (auto& ts : c->tile_slots) { dev_free(&ts.cost); dev_free(&ts.order); }
     if (c->d_io) { cudaFree(c->d_io); c->d_io = nullptr; }
     if (c->h_status) { cudaFreeHost(c->h_status); c->h_status = nullptr; }

@@ -111,6 +111,7 @@ struct bihrt_ctx {
     uint32_t* d_status_map = nullptr;                  // its device alias
     void*     d_io = nullptr; size_t io_cap = 0;      // staging for host ray lists / results
     unsigned long long* d_counters = nullptr;
+    BihNode*  d_top = nullptr;                         // TRACE_TOP_NODES experiment
     uint32_t* d_work = nullptr;                        // persistent-kernel work counter
     // cost-ordered tiles: the longest unit of every 32x32-pixel tile measured by the previous launch of the same frame
     // geometry, and the tile order (most expensive first) derived from it
@@ -136,7 +137,7 @@ struct bihrt_ctx {
     int opt_refill_threshold = 32;
     int opt_refill_incoherent = 8;
     int opt_chunk_items = 32;
-    int opt_vote_wait = 1, opt_vote_walk = 3;
+    int opt_vote_wait = 1, opt_vote_walk = 4;
     int opt_lane_groups = -1; // samples of a pixel across lanes: -1 auto (as many as divide the sample count, <= 32), else 2^k
     int opt_interleave_chunk = 8;  // multi-GPU unit interleave: consecutive units per run (power of two; reduced until it divides a tile)
     int opt_tile_order = 1; // camera modes: start the tiles that were expensive in the previous frame first (1: launches of 64 k .. 48 M rays on scenes of >= 10 k triangles, 2: always, 0: never)
@@ -178,6 +179,7 @@ struct TraceArgs {
     int gshift;             // the samples of a pixel are spread over 2^gshift consecutive lanes (camera modes)
     uint32_t* fb;
     unsigned long long* counters; uint32_t* work;
+    const BihNode* top;     // TRACE_TOP_NODES experiment: breadth-first copy of the top levels (NULL = not staged)
     uint32_t* status_map;   // mapped host word for device-detected errors (tree of the wrong kind for this kernel)
     int refill_threshold;   // lanes whose ray ended wait until this many are idle (or nobody is busy)
     int refill_incoherent;  // threshold used instead for ray-list packets with mixed direction signs
