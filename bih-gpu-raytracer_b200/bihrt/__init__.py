@@ -67,6 +67,8 @@ ABI_SYMBOLS = [
     "bihrt_build", "bihrt_refit", "bihrt_get_build_info", "bihrt_export_reference_view", "bihrt_trace", "bihrt_trace_any", "bihrt_trace_counted",
     "bihrt_render", "bihrt_render_counted", "bihrt_render_shard", "bihrt_render_samples", "bihrt_render_interleaved", "bihrt_render_interleaved_to", "bihrt_framebuffer_ipc_export", "bihrt_framebuffer_ipc_open", "bihrt_framebuffer_ipc_close", "bihrt_framebuffer_ipc_unexport", "bihrt_bih_region", "bihrt_bih_adopt", "bihrt_bih_copy", "bihrt_framebuffer_resolve", "bihrt_render_hits", "bihrt_secondary_rays", "bihrt_framebuffer", "bihrt_framebuffer_read",
     "bihrt_bih_blob_bytes", "bihrt_bih_export", "bihrt_bih_import",
+    "bihrt_create_multi", "bihrt_destroy_multi", "bihrt_multi_size", "bihrt_multi_nccl_version", "bihrt_multi_broadcast",
+    "bihrt_multi_render", "bihrt_multi_sync",
 ]
 
 _lib = None
@@ -84,6 +86,9 @@ def load_library(path=None):
         lib.bihrt_last_error.argtypes = [C.c_void_p]
         lib.bihrt_destroy.restype = None
         lib.bihrt_destroy.argtypes = [C.c_void_p]
+        lib.bihrt_destroy_multi.restype = None
+        lib.bihrt_multi_broadcast.argtypes = [C.c_void_p]
+        lib.bihrt_multi_sync.argtypes = [C.c_void_p]
         _lib = lib
     return _lib
 
@@ -422,6 +427,61 @@ class Renderer:
 
     def bih_import(self, dev_buffer, nbytes):
         self._check(self._lib.bihrt_bih_import(self._ctx, _ptr(dev_buffer), C.c_uint64(nbytes)))
+
+
+class MultiRenderer:
+    """Several GPUs of ONE process behind the C ABI (bihrt_create_multi: N contexts + one in-library NCCL communicator).
+    .ctx[0] is the builder / gatherer and behaves like a Renderer; broadcast() replicates its BIH, render() traces one
+    frame over all devices into ctx[0]'s framebuffer."""
+
+    def __init__(self, ngpu):
+        self._lib = load_library()
+        self._arr = (C.c_void_p * ngpu)()
+        self.ngpu = ngpu
+        rc = self._lib.bihrt_create_multi(self._arr, C.c_int32(ngpu))
+        if rc != OK:
+            raise BihrtError(rc, "bihrt_create_multi(%d) failed (fewer GPUs, no peer access, or libnccl.so.2 missing)" % ngpu)
+        self.ctx = []
+        for i in range(ngpu):
+            r = Renderer.__new__(Renderer)
+            r._lib, r._ctx, r.device, r.n = self._lib, C.c_void_p(self._arr[i]), i, 0
+            r.close = lambda: None              # released by the group
+            self.ctx.append(r)
+
+    def _check(self, rc):
+        self.ctx[0]._check(rc)
+
+    def nccl_version(self):
+        return self._lib.bihrt_multi_nccl_version()
+
+    def broadcast(self):
+        self._check(self._lib.bihrt_multi_broadcast(self.ctx[0]._ctx))
+        return self
+
+    def render(self, camera, w, h, spp=1, seed=1984, jitter=False):
+        cam = camera if isinstance(camera, Camera) else Camera.from_array(camera)
+        self._check(self._lib.bihrt_multi_render(self.ctx[0]._ctx, C.byref(cam), C.c_int32(w), C.c_int32(h), C.c_int32(spp),
+                                                 C.c_uint64(seed), C.c_uint32(RENDER_JITTER if jitter else 0)))
+        return self
+
+    def sync(self):
+        self._check(self._lib.bihrt_multi_sync(self.ctx[0]._ctx))
+
+    def framebuffer(self):
+        return self.ctx[0].framebuffer()
+
+    def close(self):
+        if getattr(self, "_arr", None) is not None and self._arr[0]:
+            self._lib.bihrt_destroy_multi(self._arr, C.c_int32(self.ngpu))
+            for r in self.ctx:
+                r._ctx = C.c_void_p()
+            self._arr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 from . import multi  # noqa: E402  (bihrt.multi: torch.distributed plumbing)

@@ -72,7 +72,9 @@ static_assert(sizeof(BihHeader) == 64, "header is one 64-byte line");
 // context
 // -------------------------------------------------------------------------------------------
 #define BIHRT_PROF_EVENTS 16
+struct bihrt_group;       // csrc/multi.cu: the contexts of one bihrt_create_multi call + their NCCL communicators
 struct bihrt_ctx {
+    bihrt_group* group = nullptr; int group_rank = 0;
     int          device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t own_stream = nullptr;

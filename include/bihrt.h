@@ -243,6 +243,27 @@ BIHRT_API int bihrt_bih_adopt(bihrt_ctx* ctx, int64_t n);
  * ordered after the work enqueued on src's stream and before dst's next call. */
 BIHRT_API int bihrt_bih_copy(bihrt_ctx* dst, bihrt_ctx* src);
 
+/* ---- several GPUs in ONE process ("Multi-GPU adds bihrt_create_multi(ctx**, int ngpu) which internally holds
+ *      one NCCL communicator").  The reference is single-GPU; rays are independent given a replicated tree (8(e)).
+ *      bihrt_create_multi fills ctxs[0..ngpu) with one context per device 0..ngpu-1 that share an NCCL communicator set
+ *      (ncclCommInitAll; NCCL is bound at run time from libnccl.so.2).  Context 0 is the builder and the gatherer: load the
+ *      scene and bihrt_build on it as usual, then per frame
+ *          bihrt_multi_broadcast(ctxs[0]);                    one ncclBroadcast of the BIH blob, in place, no host copy
+ *          bihrt_multi_render(ctxs[0], cam, w, h, spp, ...);   unit interleave; every device's trace kernel stores its finished
+ *                                                             pixels straight into context 0's framebuffer over NVLink
+ *          bihrt_framebuffer_read(ctxs[0], host);             ordered after every device's launch (events), same image as
+ *                                                             bihrt_render on one GPU, bit for bit
+ *      Everything is asynchronous on the contexts' streams; bihrt_multi_sync waits for all of them.  Contexts of a group are
+ *      released together with bihrt_destroy_multi (not bihrt_destroy). ----------------------------------------------------- */
+BIHRT_API int  bihrt_create_multi(bihrt_ctx** ctxs, int32_t ngpu);
+BIHRT_API void bihrt_destroy_multi(bihrt_ctx** ctxs, int32_t ngpu);
+BIHRT_API int  bihrt_multi_size(const bihrt_ctx* ctx);                       /* contexts in ctx's group (1 for a plain context) */
+BIHRT_API int  bihrt_multi_nccl_version(void);                               /* e.g. 22809; 0 if libnccl.so.2 cannot be bound */
+BIHRT_API int  bihrt_multi_broadcast(bihrt_ctx* ctx0);
+BIHRT_API int  bihrt_multi_render(bihrt_ctx* ctx0, const bihrt_camera* cam, int32_t w, int32_t h, int32_t spp,
+                                  uint64_t seed, uint32_t flags);
+BIHRT_API int  bihrt_multi_sync(bihrt_ctx* ctx0);
+
 #ifdef __cplusplus
 }
 #endif

@@ -48,13 +48,16 @@ def test_cli_two_gpus_render_the_same_frame(scenes, tmp_path):
     raw = tmp_path / "mesh.tri9"
     tri.tofile(raw)
     imgs = []
-    for g in (1, 2):
-        out = tmp_path / ("frame%d.ppm" % g)
-        p = subprocess.run([CLI, str(raw), "-w", "330", "-h", "200", "-s", "4", "-f", "2", "-g", str(g), "-o", str(out)],
-                           capture_output=True, text=True, timeout=120)
+    for k, extra in enumerate((["-g", "1"], ["-g", "2"], ["-g", "2", "-p"])):      # one GPU; bihrt_create_multi (NCCL); peer copies
+        out = tmp_path / ("frame%d.ppm" % k)
+        p = subprocess.run([CLI, str(raw), "-w", "330", "-h", "200", "-s", "4", "-f", "2"] + extra + ["-o", str(out)],
+                           capture_output=True, text=True, timeout=180)
         assert p.returncode == 0, p.stdout + p.stderr
+        if extra == ["-g", "2"]:
+            assert "bihrt_create_multi: 2 contexts" in p.stdout, p.stdout + p.stderr
         imgs.append(read_ppm(out))
     np.testing.assert_array_equal(imgs[0], imgs[1])
+    np.testing.assert_array_equal(imgs[0], imgs[2])
 
 
 def test_cli_reports_errors():

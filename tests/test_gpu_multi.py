@@ -50,7 +50,7 @@ def test_two_gpus_render_the_same_image(scenes):
     r2 = bihrt.Renderer(1)
     p0, nb0 = r0.bih_region(len(tri))
     p2, nb2 = r2.bih_region(len(tri))
-    assert nb0 == nb2 == 64 + 64 * len(tri)
+    assert nb0 == nb2 == 64 + (64 + 48) * len(tri)           # header | 64-byte node slots | 48-byte triangle records
     src = torch.as_tensor(multi._CudaView(p0, (nb0,), "|u1"), device="cuda:0")
     dst = torch.as_tensor(multi._CudaView(p2, (nb2,), "|u1"), device="cuda:1")
     r0.sync(); dst.copy_(src); torch.cuda.synchronize(0); torch.cuda.synchronize(1)
@@ -88,3 +88,33 @@ def test_interleaved_to_one_framebuffer_is_the_full_frame(scenes, spp, count):
         r.render_interleaved_to(cam, w, h, spp, k, count, None, jitter=True)
     np.testing.assert_array_equal(r.framebuffer(), full)
     r.close()
+
+
+@pytest.mark.parametrize("quality", [False, True])
+def test_create_multi_nccl_group_renders_the_same_image(scenes, quality):
+    """bihrt_create_multi: N contexts + one NCCL communicator inside the library.  Context 0 builds,
+    bihrt_multi_broadcast replicates the blob with one ncclBroadcast, bihrt_multi_render = the single-GPU frame, bit for bit,
+    for several frames with a rebuild in between (stream ordering between the devices)."""
+    import torch
+    import bihrt
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    n = min(torch.cuda.device_count(), 4)
+    n = 2 if n == 3 else n
+    w, h, spp = 330, 200, 8
+    cam = scenes.pinhole_camera(aspect=w / h)
+    single = bihrt.Renderer(0)
+    m = bihrt.MultiRenderer(n)
+    assert m.nccl_version() > 0
+    if quality:
+        single.set_option("morton_bits", 63)
+        m.ctx[0].set_option("morton_bits", 63)
+    for frame, nseg in enumerate((96, 128, 96)):
+        tri = scenes.displaced_sphere(nseg, phase=0.3 * frame)
+        want = single.load_models(tri).build().render(cam, w, h, spp=spp, seed=7 + frame, jitter=True).framebuffer().copy()
+        m.ctx[0].load_models(tri).build()
+        m.broadcast().render(cam, w, h, spp=spp, seed=7 + frame, jitter=True)
+        np.testing.assert_array_equal(m.framebuffer(), want)
+    m.sync()
+    m.close()
+    single.close()
