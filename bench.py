@@ -464,12 +464,18 @@ def run_ours(args, rank, world, local_rank):
             copy_out.wait_stream(stream)
             for k in range(k_frames):
                 b = k & 1
-                with torch.cuda.stream(copy_in):
-                    if k >= 2:
-                        copy_in.wait_event(ev_free[b])           # frame k-2's build input has been consumed
-                    dev_tri[b].copy_(pinned_tri, non_blocking=True)      # H2D on the copy stream
-                    ev_in[b].record(copy_in)
-                stream.wait_event(ev_in[b])
+                # the frame's vertices cross PCIe ONCE: rank k % N uploads them over its own link (so every link carries one
+                # upload every N frames and rank 0's link is left to the framebuffer download) and hands them to the others
+                # over NVLink -- one broadcast of 36 MB on the launching stream
+                if rank == k % world:
+                    with torch.cuda.stream(copy_in):
+                        if k >= 2:
+                            copy_in.wait_event(ev_free[b])       # frame k-2's build input has been consumed
+                        dev_tri[b].copy_(pinned_tri, non_blocking=True)      # H2D on the copy stream
+                        ev_in[b].record(copy_in)
+                    stream.wait_event(ev_in[b])
+                if world > 1:
+                    dist.broadcast(dev_tri[b], src=k % world)
                 r.update_vertices(dev_tri[b])                    # device -> the context's input array (36 MB D2D)
                 ev_free[b].record(stream)
                 r.build()
@@ -676,13 +682,14 @@ def run_ours(args, rank, world, local_rank):
                "build_ms_per_mtri": build_ms / (n_tri / 1e6), "build_ms": build_ms,
                "build_roofline": {"bound": "hbm", "algorithmic_bytes_per_triangle": 320, "achieved": n_tri * 320 / (build_ms * 1e-3) / 1e9,
                                   "peak": peak, "unit": "GB/s", "frac": n_tri * 320 / (build_ms * 1e-3) / 1e9 / peak},
-               "e2e": {"value": e2e_val, "unit": "Mrays/s", "h2d_bytes_per_step": n_tri * 36 * world, "d2h_bytes_per_step": W * H * 4,
+               "e2e": {"value": e2e_val, "unit": "Mrays/s", "h2d_bytes_per_step": n_tri * 36 if can_pipe else n_tri * 36 * world, "d2h_bytes_per_step": W * H * 4,
                        "ms_per_step": ms_e2e, "frames_timed": e2e_frames, "frame_crc32": e2e_crc,
                        "serial_value": rays_total / (ms_e2e_serial * 1e-3) / 1e6, "serial_ms_per_step": ms_e2e_serial,
-                       "what": ("every rank: vertices H2D from pinned memory over its own PCIe link (%d x 36 MB) + bihrt_build (local, deterministic) + its share of the "
-                                "frame stored into rank 0's framebuffer%s; rank 0: framebuffer D2H to pinned memory.  Pipelined frame loop: the upload of frame k+1 and the "
-                                "download of frame k-1 run on copy streams while frame k is traced (value); serial_value = the same frame with nothing overlapped" % (
-                                    world, " over NVLink + frame barrier" if world > 1 else "")) if can_pipe else
+                       "what": ("per frame: vertices H2D from pinned host memory (36 MB, by rank frame %% %d over its own PCIe link%s) + bihrt_build on every rank (local, "
+                                "deterministic: identical trees, no BIH broadcast) + every rank's share of the frame stored into rank 0's framebuffer%s; rank 0: framebuffer D2H to "
+                                "pinned memory.  Pipelined frame loop: the upload of frame k+1 and the download of frame k-1 run on copy streams while frame k is traced (value); "
+                                "serial_value = every rank uploads its own copy, nothing overlapped" % (
+                                    world, ", then one NVLink broadcast" if world > 1 else "", " over NVLink + frame barrier" if world > 1 else "")) if can_pipe else
                                "vertices H2D (pinned) + bihrt_build + render + framebuffer reduce + D2H (pinned), per frame, serial"},
                "gpu_launches": int(launches), "clocks": clocks}
         if animated:
@@ -804,6 +811,11 @@ def run_ours(args, rank, world, local_rank):
                 if nm == "shadow":      # occlusion query: is the light (t = 1) hidden -- ends at the first blocker
                     ms_o = med(lambda: r.trace_any(db, tmax=1.0, blocker=os_))
                     e["shadow_occlusion_mrays_s"] = len(db) / (ms_o * 1e-3) / 1e6
+                if nm == "bounce":      # incoherent batch: traced through the origin-cell / octant permutation (sort included in the time)
+                    r.set_option("trace_sort_rays", 1)
+                    ms_s = med(lambda: r.trace(db, t=ot, slot=os_, prim=os_))
+                    r.set_option("trace_sort_rays", 0)
+                    e["bounce_sorted_mrays_s"] = len(db) / (ms_s * 1e-3) / 1e6
                 e[nm + "_rays"] = len(db)
                 e[nm + "_generation_ms"] = med(lambda: r.secondary_rays(ca, 1920, 1080, spp=1, kind=kind, light=(0.0, 0.8, 0.0)), 3)
             e["primary_plus_shadow"] = shadow_pass(ca, 1920, 1080, 1, (0.0, 0.8, 0.0), "atrium, 1920x1080 x 1 spp: primary hits -> shadow rays -> occlusion query")

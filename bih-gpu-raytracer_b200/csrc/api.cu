@@ -140,6 +140,8 @@ void bihrt_destroy(bihrt_ctx* c) {
     dev_free(&c->d_fb); dev_free(&c->d_counters); dev_free(&c->d_work); dev_free(&c->d_top);
     for (auto& ts : c->tile_slots) { dev_free(&ts.cost); dev_free(&ts.order); }
     if (c->d_io) { cudaFree(c->d_io); c->d_io = nullptr; }
+    for (int i = 0; i < 2; i++) { dev_free(&c->d_rs_keys[i]); dev_free(&c->d_rs_vals[i]); }
+    dev_free(&c->d_rs_hist); dev_free(&c->d_rs_lookback); dev_free(&c->d_rs_hdr);
     if (c->h_status) { cudaFreeHost(c->h_status); c->h_status = nullptr; }
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -209,6 +211,7 @@ int bihrt_set_option(bihrt_ctx* c, const char* name, int64_t v) {
         if (v) for (int i = 0; i < BIHRT_PROF_EVENTS; i++) if (!c->prof_ev[i]) cudaEventCreate(&c->prof_ev[i]);
     }
     else if (!strcmp(name, "trace_lane_groups")) c->opt_lane_groups = (int)v;
+    else if (!strcmp(name, "trace_sort_rays")) c->opt_sort_rays = (int)v;
     else if (!strcmp(name, "trace_sm_queues")) c->opt_sm_queues = (int)v;
     else if (!strcmp(name, "trace_tile_sort_below")) c->opt_tile_sort_below = v;
     else if (!strcmp(name, "trace_tile_order")) { c->opt_tile_order = (int)v; for (auto& ts : c->tile_slots) ts.valid = false; }
@@ -533,6 +536,9 @@ static int trace_impl(bihrt_ctx* c, const bihrt_ray* rays, int64_t n, float* t, 
         else { BIHRT_CUDA(c, cudaMemcpyAsync(front, rays, (size_t)n * sizeof(bihrt_ray), cudaMemcpyHostToDevice, c->stream)); a.rays = (const bihrt_ray*)front; }
         a.nrays = n; a.out_t = o.t; a.out_slot = o.slot; a.out_prim = o.prim;
         a.any_hit = any_hit ? 1 : 0; a.tmax = tmax;
+        // incoherent batches (option trace_sort_rays): trace through a permutation that groups the rays by origin cell and
+        // direction octant; results still land in list order
+        if (c->opt_sort_rays && n >= 4096 && n < (1ll << 31)) { if ((rc = bihrt_ray_sort_launch(c, a.rays, n, &a.perm))) return rc; }
         if ((rc = bihrt_trace_launch(c, a, 0, counters != nullptr))) return rc;
         if ((rc = unstage_outputs(c, n, o))) return rc;
     }

@@ -114,6 +114,10 @@ struct bihrt_ctx {
     void*     d_io = nullptr; size_t io_cap = 0;      // staging for host ray lists / results
     unsigned long long* d_counters = nullptr;
     BihNode*  d_top = nullptr;                         // TRACE_TOP_NODES experiment
+    // ray sorting scratch (raysort.cu)
+    uint32_t *d_rs_keys[2] = {nullptr, nullptr}, *d_rs_vals[2] = {nullptr, nullptr}, *d_rs_hist = nullptr, *d_rs_lookback = nullptr;
+    BihHeader* d_rs_hdr = nullptr; size_t rs_cap = 0;
+    int opt_sort_rays = 0;  // ray lists: 1 = group the rays by origin cell + direction octant before tracing (incoherent batches), 0 = trace in list order
     uint32_t* d_work = nullptr;                        // persistent-kernel work counter
     // cost-ordered tiles: the longest unit of every 32x32-pixel tile measured by the previous launch of the same frame
     // geometry, and the tile order (most expensive first) derived from it
@@ -137,7 +141,7 @@ struct bihrt_ctx {
     // options
     int opt_trace_blocks_per_sm = 0;   // 0 = occupancy query
     int opt_refill_threshold = 32;
-    int opt_refill_incoherent = 8;
+    int opt_refill_incoherent = 32;   // (8 paid with the 16-byte nodes; with the children boxes an early refill of incoherent packets costs 5-10 %)
     int opt_chunk_items = 32;
     int opt_vote_wait = 1, opt_vote_walk = 4;
     int opt_lane_groups = -1; // samples of a pixel across lanes: -1 auto (as many as divide the sample count, <= 32), else 2^k
@@ -161,7 +165,14 @@ int  bihrt_fail(bihrt_ctx* c, int code, const char* fmt, ...);
 #define BIHRT_CUDA(c, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
     return bihrt_fail((c), BIHRT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
 
+// d_hist layout (uint32 words), shared by the build and the ray sort
+#define H_HIST      0        // up to 8 x 256 digit counts (4 passes for the 30-bit keys, 8 for the 63-bit keys of the quality mode)
+#define H_TILECTR   2048     // [0..7] onesweep tile counters, [8] rle tile counter
+#define H_WORDS     2064
+#define SORT_TILE   4096     // keys per onesweep tile (32-bit keys)
+
 // build.cu
+int bihrt_sort_pairs_launch(bihrt_ctx* c, uint32_t* keys[2], uint32_t* vals[2], uint32_t n, int passes, uint32_t* hist, uint32_t* lookback, BihHeader* hdr);
 int bihrt_build_launch(bihrt_ctx* c);
 int bihrt_build_launch_q(bihrt_ctx* c);
 int bihrt_refit_launch(bihrt_ctx* c);
@@ -169,6 +180,7 @@ int bihrt_refit_launch(bihrt_ctx* c);
 struct TraceArgs {
     const BihHeader* hdr; const BihNode* nodes; const BihTri* tris;
     const bihrt_ray* rays; int64_t nrays;
+    const uint32_t* perm;     // ray lists: trace ray perm[i] as the i-th item (results still go to the ray's own slot); NULL = in list order
     int any_hit; float tmax;  // ray lists: occlusion query -- some hit with 0 < t < tmax, not the closest one
     float* out_t; int32_t* out_slot; int32_t* out_prim;
     // camera mode
@@ -193,6 +205,8 @@ struct TraceArgs {
 int bihrt_trace_launch(bihrt_ctx* c, const TraceArgs& a, int mode /*0 rays,1 render fb,2 render hits*/, bool counted);
 int bihrt_resolve_launch(bihrt_ctx* c, uint32_t* fb, int npix, int spp);
 int bihrt_tile_order_launch(bihrt_ctx* c, uint32_t* cost, uint32_t* order, uint32_t ntiles, bool full_sort);
+// raysort.cu: permutation that groups a ray list by origin cell and direction octant (perm[i] = index of the i-th ray to trace)
+int bihrt_ray_sort_launch(bihrt_ctx* c, const bihrt_ray* rays, int64_t n, const uint32_t** perm);
 // shade.cu
 int bihrt_secondary_launch(bihrt_ctx* c, const float* t, const int32_t* slot, int64_t n, uint32_t* tile_cnt, unsigned long long* total,
                            const bihrt_camera& cam, int w, int h, int spp, uint64_t seed, uint32_t flags, int kind, const float light[3],

@@ -85,11 +85,6 @@ __device__ __forceinline__ void minmax3(float a, float b, float c, float& mn, fl
     if (!(c < mx)) mx = c;
 }
 
-// d_hist layout (uint32 words)
-#define H_HIST      0        // up to 8 x 256 digit counts (4 passes for the 30-bit keys, 8 for the 63-bit keys of the quality mode)
-#define H_TILECTR   2048     // [0..7] onesweep tile counters, [8] rle tile counter
-#define H_WORDS     2064
-
 // ------------------------------------------------------------------------------------------
 // also clears the look-back words of the four sort passes (one launch instead of a kernel + a memset node)
 __global__ void __launch_bounds__(256) k_init(uint32_t* hist, uint32_t* enc, BihHeader* hdr, uint32_t n, uint4* __restrict__ lookback, uint32_t lb_vec4, uint32_t status0, uint32_t quality) {
@@ -348,6 +343,25 @@ __global__ void __launch_bounds__(OS_THREADS) k_onesweep(const K* __restrict__ k
             vals_out[dst] = s_vals[j];
         }
     }
+}
+
+// The same sort for other 32-bit key / value pairs (ray sorting, csrc/raysort.cu): `passes` 8-bit passes starting at bit 0,
+// hist = digit histograms of keys[0] (layout above) with zeroed tile counters, lookback = passes x tiles x 256 zeroed words.
+// The sorted pairs end in buffer passes & 1.
+int bihrt_sort_pairs_launch(bihrt_ctx* c, uint32_t* keys[2], uint32_t* vals[2], uint32_t n, int passes, uint32_t* hist, uint32_t* lookback, BihHeader* hdr) {
+    const uint32_t os_tiles = (n + OS_TILE - 1) / OS_TILE;
+    int cur = 0;
+    for (int pass = 0; pass < passes; pass++) {
+        uint32_t* lb = lookback + (size_t)pass * os_tiles * 256;
+        if (pass == 0)
+            k_onesweep<uint32_t, OS_ITEMS, true><<<os_tiles, OS_THREADS, 0, c->stream>>>(keys[cur], nullptr, keys[cur ^ 1], vals[cur ^ 1], n, pass, hist, lb, hdr);
+        else
+            k_onesweep<uint32_t, OS_ITEMS, false><<<os_tiles, OS_THREADS, 0, c->stream>>>(keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], n, pass, hist, lb, hdr);
+        cur ^= 1;
+    }
+    c->kernel_launches += passes;
+    BIHRT_CUDA(c, cudaGetLastError());
+    return BIHRT_OK;
 }
 
 // ------------------------------------------------------------------------------------------

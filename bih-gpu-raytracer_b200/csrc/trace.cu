@@ -349,6 +349,8 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
                         item = ray < (uint64_t)a.nrays ? ray : ~0ull;        // padding of the last chunk
                         if (item == ~0ull) want_item = true;
                     }
+                    // sorted ray lists: the i-th item is ray perm[i]; from here on `item` is the ray's own index (load and store)
+                    if (MODE == 0 && a.perm && item != ~0ull) item = __ldg(a.perm + item);
                     if (MODE != 0) {
                         const uint64_t pix = item >> gshift;
                         s0 = a.s_begin + (int)((uint32_t)item & ((1u << gshift) - 1u)) * nsamp;

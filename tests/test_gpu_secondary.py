@@ -61,3 +61,39 @@ def test_secondary_rays(renderer, scenes, oracle, scene):
             np.testing.assert_array_equal(blk >= 0, (s0 >= 0) & (t0 < np.float32(tmax)))
             assert blk.max() < len(tri)
         np.testing.assert_array_equal(renderer.trace_any(rays, tmax=1.0) >= 0, (s0 >= 0) & (t0 < 1.0))      # host buffers
+
+
+@pytest.mark.parametrize("n_rays", [5000, 70001, 1 << 20])
+def test_sorted_ray_lists_give_the_same_results_in_list_order(renderer, scenes, oracle, n_rays):
+    """Option trace_sort_rays: the list is traced through a permutation (origin cell + direction octant, 3 onesweep passes) but
+    every result lands in the ray's own slot: outputs equal the unsorted trace's -- and the oracle's -- bit for bit,
+    for closest hits, occlusion queries, counters (same rays, same per-ray work), device and host buffers."""
+    import torch
+    tri = scenes.atrium(0.2)
+    ob = oracle.Bih(tri)
+    renderer.load_models(tri).build()
+    rng = np.random.default_rng(n_rays)
+    # incoherent rays: origins all over the hall (some outside the scene box), random directions, a few axis-parallel
+    o = rng.uniform([-2.2, -1.1, -1.1], [2.2, 1.1, 1.1], (n_rays, 3))
+    d = rng.normal(size=(n_rays, 3))
+    d[::97, 0] = 0.0
+    rays = np.ascontiguousarray(np.concatenate([o, d], 1), dtype=np.float32)
+    t0, s0, p0, c0 = renderer.trace(rays, counted=True)
+    renderer.set_option("trace_sort_rays", 1)
+    t1, s1, p1, c1 = renderer.trace(rays, counted=True)
+    t2, s2, p2 = renderer.trace(rays)
+    d_rays = torch.from_numpy(rays).cuda()
+    t3, s3, p3 = renderer.trace(d_rays)
+    blk = renderer.trace_any(d_rays, tmax=0.7)
+    renderer.set_option("trace_sort_rays", 0)
+    blk0 = renderer.trace_any(d_rays, tmax=0.7)
+    for (t, s, p) in ((t1, s1, p1), (t2, s2, p2), (t3.cpu().numpy(), s3.cpu().numpy(), p3.cpu().numpy())):
+        np.testing.assert_array_equal(s, s0)
+        np.testing.assert_array_equal(t, t0)
+        np.testing.assert_array_equal(p, p0)
+    assert c1["nodes"] == c0["nodes"] and c1["tris"] == c0["tris"]
+    np.testing.assert_array_equal(blk.cpu().numpy() >= 0, blk0.cpu().numpy() >= 0)
+    if n_rays <= 70001:
+        tr, sr, pr = ob.trace(rays, "ref")
+        np.testing.assert_array_equal(s0, sr)
+        np.testing.assert_array_equal(t0, tr)
