@@ -584,7 +584,10 @@ __device__ __forceinline__ void node_store(BihNode* __restrict__ nd, int axis, u
     p[3] = make_float4(br[2], br[3], br[4], br[5]);
 }
 
-__global__ void __launch_bounds__(128) k_nodes(const uint32_t* __restrict__ umc, const uint32_t* __restrict__ first,
+#ifndef NODES_BLOCK
+#define NODES_BLOCK 128
+#endif
+__global__ void __launch_bounds__(NODES_BLOCK) k_nodes(const uint32_t* __restrict__ umc, const uint32_t* __restrict__ first,
                                                BihHeader* hdr, const float4* __restrict__ heaps, uint32_t P,
                                                BihNode* __restrict__ nodes, uint32_t* __restrict__ status_map) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -828,7 +831,7 @@ int bihrt_build_launch(bihrt_ctx* c) {
         launches++;
     }
     PROF_MARK();   // 10: after upper heap levels
-    k_nodes<<<(n + 127) / 128, 128, 0, st>>>(c->d_umc, c->d_first, c->d_hdr, c->d_heaps, P, c->d_nodes, c->d_status_map);
+    k_nodes<<<(n + NODES_BLOCK - 1) / NODES_BLOCK, NODES_BLOCK, 0, st>>>(c->d_umc, c->d_first, c->d_hdr, c->d_heaps, P, c->d_nodes, c->d_status_map);
     PROF_MARK();   // 11: after nodes
     PROF_MARK();   // 12: after reorder
     c->prof_count = pe;
@@ -866,7 +869,7 @@ int bihrt_refit_launch(bihrt_ctx* c) {
         k_heap_up<<<(used + 255) / 256, 256, 0, st>>>(c->d_heaps, P, lvl, used);
         launches++;
     }
-    k_nodes<<<(n + 127) / 128, 128, 0, st>>>(c->d_umc, c->d_first, c->d_hdr, c->d_heaps, P, c->d_nodes, c->d_status_map);
+    k_nodes<<<(n + NODES_BLOCK - 1) / NODES_BLOCK, NODES_BLOCK, 0, st>>>(c->d_umc, c->d_first, c->d_hdr, c->d_heaps, P, c->d_nodes, c->d_status_map);
     c->kernel_launches += 5 + launches;
     BIHRT_CUDA(c, cudaGetLastError());
     return BIHRT_OK;
