@@ -66,6 +66,7 @@
 #define TRACE_TOP_NODES 0
 #endif
 #define TOP_FLAG 0x40000000u
+#define BOX_EPS 2.384185791015625e-07f      /* 2^-22: relative (and, times |o/d|, absolute) margin of the box tests */
 
 // (double)det < 0.000001 (R/src/CUDAKernels.cu:28)  <=>  det < 0x358637be as binary32
 #define DET_EPS __uint_as_float(0x358637beu)
@@ -183,7 +184,10 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
     uint64_t item = ~0ull;                     // current work item, ~0 = none
     int s = 0, s0 = 0;                         // sample of the item being traced, first sample of the item
     uint32_t hits = 0, pixel = 0, pxy = 0;
-    float ox = 0.f, oy = 0.f, oz = 0.f, ix = 1.f, iy = 1.f, iz = 1.f;      // origin and 1/direction (the boxes need all three axes)
+    // the box tests need all three axes: 1/direction, -origin/direction (plane distance = one FMA) and the absolute rounding
+    // margin that goes with it; origin and direction themselves are only needed per axis (plane test) and by the triangle
+    // test, and live in shared memory
+    float ix = 1.f, iy = 1.f, iz = 1.f, nx = 0.f, ny = 0.f, nz = 0.f, bpad = 0.f;
     uint32_t cur = NONE;                       // item being walked: node index, leaf|slot, or NONE
     float rMin = 0.f, pMin = 0.f, pMax = 0.f;
     Hit h; h.t = FLT_MAX; h.slot = -1;
@@ -370,7 +374,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
             }
             // start the next ray of every idle lane that owns an item
             if (cur == NONE && item != ~0ull) {
-                float dx, dy, dz;
+                float ox, oy, oz, dx, dy, dz;
                 if (MODE == 0) {
                     const float* p = reinterpret_cast<const float*>(a.rays + item);
                     ox = __ldg(p); oy = __ldg(p + 1); oz = __ldg(p + 2); dx = __ldg(p + 3); dy = __ldg(p + 4); dz = __ldg(p + 5);
@@ -388,6 +392,11 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
                 }
                 // Ray::Ray, R/src/Ray.cu:3-10
                 ix = __frcp_rn(dx); iy = __frcp_rn(dy); iz = __frcp_rn(dz);
+                // box planes: t = fma(plane, 1/d, -(o/d)).  The rounding of o/d is an ABSOLUTE error of 2^-24 |o/d| in t (it does not
+                // shrink with t): bpad = 2^-22 x the largest finite |o/d| widens every box interval by four times that bound.
+                nx = -__fmul_rn(ox, ix); ny = -__fmul_rn(oy, iy); nz = -__fmul_rn(oz, iz);
+                bpad = __fmul_rn(BOX_EPS, fmaxf(fmaxf(fabsf(nx) <= FLT_MAX ? fabsf(nx) : 0.f, fabsf(ny) <= FLT_MAX ? fabsf(ny) : 0.f),
+                                                fabsf(nz) <= FLT_MAX ? fabsf(nz) : 0.f));
                 if (MODE == 0 && fresh) {
                     // ray lists: a packet whose directions disagree in sign is incoherent (diffuse bounces);
                     // there, lanes that finish early are worth refilling before the whole packet has drained
@@ -442,16 +451,15 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
         // come off the stack -- h.t may have shrunk since they were pushed -- are checked (POP_VALID); an
         // item that fails is dropped without a node fetch.  Same visits, same order, same counters as the
         // entry check of oracle/bih_oracle.c:traverse_proper.
-#define BOX_EPS 2.384185791015625e-07f      /* 2^-22 */
 #define BOX_SLAB(lx, ly, lz, hx, hy, hz, bn, bf)                                                            \
         do {                                                                                                \
-            const float ax0 = __fmul_rn(__fsub_rn((lx), ox), ix), ax1 = __fmul_rn(__fsub_rn((hx), ox), ix); \
-            const float ay0 = __fmul_rn(__fsub_rn((ly), oy), iy), ay1 = __fmul_rn(__fsub_rn((hy), oy), iy); \
-            const float az0 = __fmul_rn(__fsub_rn((lz), oz), iz), az1 = __fmul_rn(__fsub_rn((hz), oz), iz); \
+            const float ax0 = __fmaf_rn((lx), ix, nx), ax1 = __fmaf_rn((hx), ix, nx);                       \
+            const float ay0 = __fmaf_rn((ly), iy, ny), ay1 = __fmaf_rn((hy), iy, ny);                       \
+            const float az0 = __fmaf_rn((lz), iz, nz), az1 = __fmaf_rn((hz), iz, nz);                       \
             const float n_ = fmaxf(fmaxf(fminf(ax0, ax1), fminf(ay0, ay1)), fminf(az0, az1));               \
             const float f_ = fminf(fminf(fmaxf(ax0, ax1), fmaxf(ay0, ay1)), fmaxf(az0, az1));               \
-            (bn) = __fmaf_rn(-fabsf(n_), BOX_EPS, n_);                                                      \
-            (bf) = __fmaf_rn(fabsf(f_), BOX_EPS, f_);                                                       \
+            (bn) = __fmaf_rn(-fabsf(n_), BOX_EPS, __fsub_rn(n_, bpad));                                     \
+            (bf) = __fmaf_rn(fabsf(f_), BOX_EPS, __fadd_rn(f_, bpad));                                      \
         } while (0)
 #define POP_VALID()                                                                                         \
         do {                                                                                                \
@@ -533,7 +541,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
             const char* tp;
             asm("mad.wide.u32 %0, %1, 12, %2;" : "=l"(tp) : "r"(cur & 0x7FFFFFFCu), "l"(tris_b));
             const float2 dxy = *reinterpret_cast<const float2*>(my_ray + 6);
-            test_leaf<COUNTED>(tp, ox, oy, oz, dxy.x, dxy.y, my_ray[8], h, ntris, wleaf);
+            test_leaf<COUNTED>(tp, my_ray[0], my_ray[2], my_ray[4], dxy.x, dxy.y, my_ray[8], h, ntris, wleaf);
             if (MODE == 0 && a.any_hit && h.slot >= 0) { STACK_RESET(); cur = NONE; }      // occluded: nothing else to learn
             else POP_VALID();
         }

@@ -512,18 +512,31 @@ static void traverse_proper(const orc_scene* s, const orc_ray* r, orc_hit* rec, 
  * box.  The boxes are exact min / max of vertex coordinates, so the leaves entered are a SUBSET of traverse_proper's, in
  * the same order: a leaf is skipped only when the ray cannot hit a triangle in it before the closest hit so far -- the
  * result equals traverse_proper's (and hence TraverseTree's) except where Moller-Trumbore's rounded t disagrees with a
- * rounded box distance by more than the 2^-22 relative margin, i.e. on grazing edge / vertex hits (the documented tie
+ * rounded box distance by more than the 2^-22 margin (relative to t and to |o/d|), i.e. on grazing edge / vertex hits (the documented tie
  * class).  Same arithmetic, operation order and NaN behaviour as the kernel, so GPU results and counters are compared
  * bit for bit against this mode; tests/test_oracle_semantics.py ties it back to traverse_ref. */
 #define BOX_EPS 2.384185791015625e-07f      /* 2^-22 */
-static inline void box_slab(const float* b /* lo.xyz hi.xyz */, const orc_ray* r, float* bn, float* bf) {
-    float ax0 = (b[0] - r->o[0]) * r->inv[0], ax1 = (b[3] - r->o[0]) * r->inv[0];
-    float ay0 = (b[1] - r->o[1]) * r->inv[1], ay1 = (b[4] - r->o[1]) * r->inv[1];
-    float az0 = (b[2] - r->o[2]) * r->inv[2], az1 = (b[5] - r->o[2]) * r->inv[2];
+/* plane distance as ONE fused multiply-add: t = fma(plane, 1/d, -(o/d)).  The rounding of o/d is an absolute error of
+ * 2^-24 |o/d| in t, so every box interval is widened by pad = 2^-22 x the largest finite |o/d| of the ray, and by 2^-22
+ * relative for the rounding of the FMA itself. */
+typedef struct { float n[3], pad; } orc_boxray;
+static inline void make_boxray(orc_boxray* q, const orc_ray* r) {
+    float m = 0.0f;
+    for (int k = 0; k < 3; k++) {
+        q->n[k] = -(r->o[k] * r->inv[k]);
+        float a = fabsf(q->n[k]);
+        m = dev_fmaxf(m, a <= FLT_MAX ? a : 0.0f);
+    }
+    q->pad = BOX_EPS * m;
+}
+static inline void box_slab(const float* b /* lo.xyz hi.xyz */, const orc_ray* r, const orc_boxray* q, float* bn, float* bf) {
+    float ax0 = fmaf(b[0], r->inv[0], q->n[0]), ax1 = fmaf(b[3], r->inv[0], q->n[0]);
+    float ay0 = fmaf(b[1], r->inv[1], q->n[1]), ay1 = fmaf(b[4], r->inv[1], q->n[1]);
+    float az0 = fmaf(b[2], r->inv[2], q->n[2]), az1 = fmaf(b[5], r->inv[2], q->n[2]);
     float n_ = dev_fmaxf(dev_fmaxf(dev_fminf(ax0, ax1), dev_fminf(ay0, ay1)), dev_fminf(az0, az1));
     float f_ = dev_fminf(dev_fminf(dev_fmaxf(ax0, ax1), dev_fmaxf(ay0, ay1)), dev_fmaxf(az0, az1));
-    *bn = fmaf(-fabsf(n_), BOX_EPS, n_);
-    *bf = fmaf(fabsf(f_), BOX_EPS, f_);
+    *bn = fmaf(-fabsf(n_), BOX_EPS, n_ - q->pad);
+    *bf = fmaf(fabsf(f_), BOX_EPS, f_ + q->pad);
 }
 
 static void traverse_box(const orc_scene* s, const float* cbox /* 12 floats per node: left box, right box */,
@@ -536,6 +549,8 @@ static void traverse_box(const orc_scene* s, const float* cbox /* 12 floats per 
     struct { int ref; float rMin, pMin, pMax; } stack[64];
     int sp = 0;
     int cur = 0;
+    orc_boxray q;
+    make_boxray(&q, r);
     for (;;) {
         int next = 0;
         if (pMin <= dev_fminf(pMax, (float)rec->t)) {
@@ -556,8 +571,8 @@ static void traverse_box(const orc_scene* s, const float* cbox /* 12 floats per 
                 float nMax = dev_fminf(pMax, tn);
                 float fMin = dev_fmaxf(pMin, tf);
                 float bn[2], bf[2];
-                box_slab(cbox + 12 * (int64_t)cur, r, &bn[0], &bf[0]);
-                box_slab(cbox + 12 * (int64_t)cur + 6, r, &bn[1], &bf[1]);
+                box_slab(cbox + 12 * (int64_t)cur, r, &q, &bn[0], &bf[0]);
+                box_slab(cbox + 12 * (int64_t)cur + 6, r, &q, &bn[1], &bf[1]);
                 float nLo = dev_fmaxf(pMin, bn[near]), nHi = dev_fminf(nMax, bf[near]);
                 float fLo = dev_fmaxf(fMin, bn[far]), fHi = dev_fminf(pMax, bf[far]);
                 int go_near = (rMin < tn) && (nLo <= nHi);
