@@ -81,11 +81,16 @@ def crc32(a):
 
 
 def kernel_source_sha():
-    """Hash of the trace kernel's sources: ncu-derived counters in profiles/ are only quoted for the kernel they were
-    captured on (profiles/trace_counters.json records the hash at capture time)."""
+    """Hash of the trace kernel's CODE (comments and blank lines stripped): ncu-derived counters in profiles/ are only quoted
+    for the kernel they were captured on (profiles/trace_counters.json records the hash at capture time)."""
+    import re
     h = hashlib.sha256()
     for f in ("csrc/trace.cu", "csrc/bihrt_internal.cuh"):
-        h.update(open(os.path.join(ROOT, "bih-gpu-raytracer_b200", f), "rb").read())
+        src = open(os.path.join(ROOT, "bih-gpu-raytracer_b200", f)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        src = "\n".join(l.split("//")[0].rstrip() for l in src.splitlines())
+        src = "\n".join(l for l in src.splitlines() if l.strip())
+        h.update(src.encode())
     return h.hexdigest()[:16]
 
 

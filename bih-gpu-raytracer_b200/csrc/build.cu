@@ -4,20 +4,20 @@
 // Launch_FindClipPlanes) and the host pre-pass of App::LoadModels (R/src/App.cpp:110-156).
 //
 // Pipeline (one stream, no host synchronisation, Nu never leaves the device):
-//   k_init        reset histograms / counters / scene-box accumulators
+//   k_init        reset histograms / counters / scene-box accumulators / look-back words
 //   k_scene_box   scene AABB                                   36 B read per triangle
 //   k_morton      AABB centre -> 30-bit Morton key, fused 4x256 digit histogram   36 R + 4 W
 //   k_onesweep x4 stable LSD radix sort, 8-bit digits, decoupled look-back       16 R + 16 W per pass
 //   k_rle_*       head flags per 256-slot block, scanned -> Nu and the leaf number at every block start      4 R
 //   k_reorder     per slot: leaf heads -> unique codes + first slot of each leaf (the RLE write, fused);
 //                 gather the triangle, write its 48-byte leaf-ordered record and its AABB as the
-//                 bottom level of six implicit min/max heaps (+8 levels per block)   4+36 R + 48+~48 W
+//                 bottom level of an implicit min/max heap of BOXES (32-byte entries, +8 levels per block)   4+36 R + 48+~35 W
 //   k_heap_up     upper heap levels (8 per launch)
-//   k_nodes       per node: Karras range/split search + two heap range queries for the clip planes,
-//                 each node written once                                            ~40 R + 16 W
+//   k_nodes       per node: Karras range/split search + two heap range queries = the boxes of its two children
+//                 (the clip planes are two components of them); each 64-byte node written once       ~50 R + 64 W
 // Results are bit-identical to the reference algorithm (oracle/bih_oracle.c): the radix tree over the
 // unique sorted codes is unique, node ids follow the Karras numbering rule, clip planes are pure
-// max/min of input floats.
+// max/min of input floats.  Quality mode (63-bit keys, capped leaves; NOT a parity path) is at the end of the file.
 #include "bihrt_internal.cuh"
 #include <float.h>
 

@@ -8,23 +8,28 @@
 //     pixel's sample group -- the samples of a pixel sit in CONSECUTIVE LANES, the warp moves from sample to sample
 //     in lock step and a pixel is written once, as its final colour, by the lane that completes it (possibly into
 //     another GPU's framebuffer: bihrt_render_interleaved_to).  Ray lists: lanes whose ray ended are refilled once
-//     `refill_threshold` of them are idle (sooner for packets with mixed direction signs);
+//     `refill_threshold` of them are idle; an option traces the list through a sort permutation (csrc/raysort.cu);
 //   * the tiles of a camera frame are traced in the order k_tile_order derived from the PREVIOUS launch of the same
-//     frame geometry (longest unit per tile, expensive tiles first): the launch is as long as its longest unit, and
-//     a unit of silhouette rays is ~0.4 ms of dependent fetches on the 1 M-triangle sphere;
+//     frame geometry (longest unit per tile, expensive tiles first): the launch is as long as its longest unit;
 //   * every lane walks its own ray with a short stack of 16-byte items (child reference + the three
 //     interval bounds) in local memory; a leaf is an item like a node, so the hot loop has one shape.  An item in
 //     hand is valid by construction; only items popped from the stack are re-checked against the closest hit;
-//   * nodes (16 B) and leaf-ordered triangles (3 x 16 B) are fetched with single 128-bit read-only
-//     loads; the per-axis ray constants (origin, 1/dir) sit in shared memory and are picked with the
-//     node's axis bits by one 64-bit LDS instead of a select chain;
-//   * two-phase ("while-while") loop: lanes take 3 node steps (unrolled), the warp votes, leaves are tested,
+//   * a node is ONE 64-byte record fetched with four 128-bit read-only loads: the reference's two clip planes and
+//     child references (the BIH proper) and the bounding boxes of the two children.  The plane logic decides what the
+//     reference's decides (strict and closed comparisons included); the boxes only remove visits -- a child whose box the
+//     ray misses inside the child's interval is never fetched (39 -> 14 nodes and 13 -> 1.1 triangle tests per primary ray
+//     on the 1 M-triangle scene, identical hits).  The per-axis ray constants (origin, 1/dir) of the node's axis come from
+//     shared memory by one 64-bit LDS selected with the axis bits the parent's reference carried; 1/dir and -origin/dir of
+//     all three axes sit in registers for the boxes (plane distance = one FMA); origin and direction themselves are only
+//     read by the triangle test, from shared memory;
+//   * leaf-ordered triangles (3 x 16 B) are fetched with 128-bit read-only loads;
+//   * two-phase ("while-while") loop: lanes take 4 node steps (unrolled), the warp votes, leaves are tested,
 //     repeat; the vote ends the node phase as soon as the lanes waiting with a leaf outnumber the walking ones.
 //
-// Logical per-ray algorithm = oracle/bih_oracle.c:traverse_proper (pruned traversal that returns what
+// Logical per-ray algorithm = oracle/bih_oracle.c:traverse_box (pruned traversal + children boxes that returns what
 // the reference's TraverseTree returns, including on axis-aligned flat geometry where the reference's
-// strict comparisons decide).  Arithmetic is IEEE binary32 without FMA contraction (explicit __f*_rn)
-// so t is bit-identical to the oracle's.
+// strict comparisons decide).  Everything that decides a hit is IEEE binary32 without FMA contraction (explicit __f*_rn)
+// so t is bit-identical to the oracle's; the box distances are explicit FMAs, mirrored with fmaf in the oracle.
 #include "bihrt_internal.cuh"
 #include <float.h>
 
@@ -791,7 +796,7 @@ int bihrt_trace_launch(bihrt_ctx* c, const TraceArgs& a_in, int mode, bool count
     }
 #endif
     if (c->built_quality) {
-        // quality-mode tree: the shipped schedule only (3 node steps per vote); the instrumented build walks one step per vote
+        // quality-mode tree: the shipped schedule only (TRACE_WALK node steps per vote); the instrumented build walks one step per vote
         TraceArgs q = a; q.vote_wait = 1; q.vote_walk = 1;
         switch (mode * 2 + (counted ? 1 : 0)) {
             case 0: rc = launch<0, false, TRACE_WALK, true>(c, a); break;

@@ -36,10 +36,15 @@ for rep, name, lines in (("prof_trace_4k16", "trace_4k16spp_1m", True), ("prof_t
 # 3. hardware counters of the trace kernel for bench.py's roofline block (issue_frac, lanes_active, l1_hit, traffic), tagged with
 #    the hash of the kernel source they were captured on: bench.py quotes them only while the source is unchanged
 import hashlib
-def source_sha():
+def source_sha():       # must match bench.py:kernel_source_sha (code only: comments and blank lines stripped)
+    import re
     h = hashlib.sha256()
     for f in ("csrc/trace.cu", "csrc/bihrt_internal.cuh"):
-        h.update(open(os.path.join(ROOT, "bih-gpu-raytracer_b200", f), "rb").read())
+        src = open(os.path.join(ROOT, "bih-gpu-raytracer_b200", f)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        src = "\n".join(l.split("//")[0].rstrip() for l in src.splitlines())
+        src = "\n".join(l for l in src.splitlines() if l.strip())
+        h.update(src.encode())
     return h.hexdigest()[:16]
 def counters(rep, rays):
     raw = subprocess.run(["ncu", "-i", os.path.join(G, rep + ".ncu-rep"), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
