@@ -115,7 +115,7 @@ int bihrt_create(bihrt_ctx** out, const bihrt_config* cfg) {
     cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1);
     int rc = 0;
     rc |= dev_alloc(c, &c->d_hist, 4096);
-    rc |= dev_alloc(c, &c->d_scenebox_enc, 8);
+    rc |= dev_alloc(c, &c->d_scenebox_enc, 24);
     rc |= dev_alloc(c, &c->d_counters, 8);
     rc |= dev_alloc(c, &c->d_work, 1024);
     // hdr->status of the last build, mirrored by the build's last kernel into mapped host memory: the host can look at it
@@ -124,6 +124,7 @@ int bihrt_create(bihrt_ctx** out, const bihrt_config* cfg) {
         cudaHostGetDevicePointer((void**)&c->d_status_map, c->h_status, 0) != cudaSuccess) { cudaGetLastError(); rc |= 1; }
     else *c->h_status = 0;
     if (rc) { bihrt_destroy(c); return BIHRT_ERR_NOMEM; }
+    if (bihrt_build_setup(c) != BIHRT_OK) { bihrt_destroy(c); return BIHRT_ERR_CUDA; }
     *out = c;
     return BIHRT_OK;
 }

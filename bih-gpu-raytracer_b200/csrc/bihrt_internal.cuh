@@ -174,6 +174,7 @@ int  bihrt_fail(bihrt_ctx* c, int code, const char* fmt, ...);
 // build.cu
 int bihrt_sort_pairs_launch(bihrt_ctx* c, uint32_t* keys[2], uint32_t* vals[2], uint32_t n, int passes, uint32_t* hist, uint32_t* lookback, BihHeader* hdr);
 int bihrt_build_launch(bihrt_ctx* c);
+int bihrt_build_setup(bihrt_ctx* c);      // once per context: scene-box accumulators and grid-barrier words in their rest state
 int bihrt_build_launch_q(bihrt_ctx* c);
 int bihrt_refit_launch(bihrt_ctx* c);
 // trace.cu

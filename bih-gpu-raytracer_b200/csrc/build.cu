@@ -22,6 +22,7 @@
 #include <float.h>
 
 #define FULL 0xffffffffu
+#define ENC_AUX 12          // d_scenebox_enc words 0..11: the two alternating accumulators of k_front; 12..17: quality mode / refit
 
 // ------------------------------------------------------------------------------------------
 // small block-level helpers (256 threads)
@@ -151,11 +152,16 @@ __device__ __forceinline__ uint32_t expand_bits10(uint32_t v) {
     v = (v * 0x00000005u) & 0x49249249u;
     return v;
 }
-__device__ __forceinline__ uint32_t morton_axis(float mn, float mx, float slo, float shi) {
-    float centre = __fmul_rn(__fadd_rn(mn, mx), 0.5f);    // == (mn + mx) / 2.0f exactly (scaling by a power of two)
+__device__ __forceinline__ float centre_of(float mn, float mx) {
+    return __fmul_rn(__fadd_rn(mn, mx), 0.5f);            // == (mn + mx) / 2.0f exactly (scaling by a power of two)
+}
+__device__ __forceinline__ uint32_t morton_axis_c(float centre, float slo, float shi) {
     float nrm = __fdiv_rn(__fsub_rn(centre, slo), __fsub_rn(shi, slo));
     float q = fminf(fmaxf(__fmul_rn(nrm, 1024.0f), 0.0f), 1023.0f);   // fmaxf(NaN,0)=0: flat axis -> cell 0
     return expand_bits10(__float2uint_rz(q));
+}
+__device__ __forceinline__ uint32_t morton_axis(float mn, float mx, float slo, float shi) {
+    return morton_axis_c(centre_of(mn, mx), slo, shi);
 }
 
 __device__ __forceinline__ uint32_t morton_of_tri(const float* t, const float slo[3], const float shi[3]) {
@@ -226,11 +232,203 @@ __global__ void __launch_bounds__(256) k_morton(const float* __restrict__ tri, u
 }
 
 // ------------------------------------------------------------------------------------------
+// k_front = k_init + k_scene_box + k_morton in ONE cooperative launch (the parity path; the quality mode and the refit keep
+// the three kernels).  All CTAs are co-resident, so a grid barrier can stand where the kernel boundary was:
+//   phase 0  clear the digit histograms, tile counters and look-back words of this build, reset the OTHER scene-box accumulator
+//            (two accumulators alternate between builds: nothing has to be cleared before the first atomic of this one)
+//   phase 1  scene box; with KEEP the centre of every triangle's AABB stays in shared memory
+//   -------  grid barrier
+//   phase 2  Morton keys + digit histograms, from the kept centres (the input is read ONCE, 36 B per triangle) or, for scenes
+//            whose centres do not fit (n > ~1.8 M), from a second read of the input
+// At 1 M triangles: 4 + 11 + 14 us of three launches -> one launch.
+// ------------------------------------------------------------------------------------------
+#define H_BAR    3000      // d_hist words [H_BAR] = arrivals, [H_BAR + 1] = generation of the grid barrier (self-resetting)
+#define H_EPOCH  3002      // builds started on this context: selects the scene-box accumulator enc[(epoch & 1) * 6 ..]
+#define FRONT_THREADS 256
+#define FRONT_STAGE_BYTES (8 * 288 * 16)              // load_quads_warp staging, one 4608-byte buffer per warp
+#define FRONT_KEEP_BYTES_PER_ITER (FRONT_THREADS * 48) // 4 triangles x 3 centre floats per thread and iteration
+#define FRONT_MAX_KEEP_ITERS 6
+
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
+    uint32_t v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+// Barrier over all CTAs of a cooperative launch.  bar[0] counts arrivals and is back at 0 when the barrier opens, bar[1] is the
+// generation the waiting CTAs spin on, so the words never need a reset between launches.
+__device__ __forceinline__ void grid_barrier(uint32_t* bar, uint32_t G) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t gen = ld_relaxed(bar + 1);
+        uint32_t old;
+        asm volatile("atom.add.release.gpu.global.u32 %0, [%1], 1;" : "=r"(old) : "l"(bar) : "memory");
+        if (old == G - 1) {
+            st_relaxed(bar, 0u);
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(bar + 1), "r"(gen + 1u) : "memory");
+        } else {
+            while (ld_acquire_u32(bar + 1) == gen) { }
+        }
+    }
+    __syncthreads();
+}
+
+template <bool KEEP>
+__global__ void __launch_bounds__(FRONT_THREADS, 2) k_front(const float* __restrict__ tri, uint32_t n, uint32_t* __restrict__ enc2,
+                                                            uint32_t* __restrict__ keys, uint32_t* __restrict__ hist, BihHeader* hdr,
+                                                            uint4* __restrict__ lookback, uint32_t lb_vec4, uint32_t status0) {
+    extern __shared__ float4 s_dyn[];
+    float4 (*s_stage)[288] = reinterpret_cast<float4 (*)[288]>(s_dyn);
+    float* s_centre = reinterpret_cast<float*>(s_dyn) + FRONT_STAGE_BYTES / 4;      // [iter][12][FRONT_THREADS]
+    __shared__ uint32_t s_hist[4 * 256];
+    __shared__ float s_red[8][6];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t G = gridDim.x;
+    const uint32_t epoch = ld_relaxed(hist + H_EPOCH);          // read before this CTA arrives at the barrier; bumped after it
+    uint32_t* enc = enc2 + (epoch & 1u) * 6u;
+    // ---- phase 0
+    for (uint32_t i = blockIdx.x * FRONT_THREADS + tid; i < lb_vec4; i += G * FRONT_THREADS) lookback[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < 1024; i += FRONT_THREADS) s_hist[i] = 0;
+    if (blockIdx.x == 0) {
+        for (int i = tid; i < H_WORDS; i += FRONT_THREADS) hist[i] = 0;
+        uint32_t* other = enc2 + ((epoch & 1u) ^ 1u) * 6u;
+        if (tid < 3) { other[tid] = 0xFFFFFFFFu; other[3 + tid] = 0u; }
+        if (tid == 0) { hdr->n = n; hdr->nu = 0; hdr->status = status0; hdr->root_axis = 0; hdr->quality = 0u; }
+    }
+    // ---- phase 1: scene AABB (R/src/App.cpp:103-106,133-137) and, with KEEP, the centre of every triangle's AABB (:128-131)
+    float lo[3] = { INFINITY, INFINITY, INFINITY }, hi[3] = { -INFINITY, -INFINITY, -INFINITY };
+    const uint32_t nq = n >> 2;
+    {
+        int it = 0;
+        for (uint32_t q0 = blockIdx.x * FRONT_THREADS + (tid & ~31u); q0 < nq; q0 += G * FRONT_THREADS, it++) {
+            float v[36];
+            load_quads_warp(tri, q0, nq, s_stage[warp], lane, v);
+            if (q0 + lane < nq) {
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+#pragma unroll
+                    for (int k = 0; k < 3; k++) {
+                        float mn, mx;
+                        minmax3(v[9 * t + k], v[9 * t + 3 + k], v[9 * t + 6 + k], mn, mx);
+                        lo[k] = fminf(lo[k], mn); hi[k] = fmaxf(hi[k], mx);
+                        if (KEEP) s_centre[(it * 12 + t * 3 + k) * FRONT_THREADS + tid] = centre_of(mn, mx);
+                    }
+                }
+            }
+        }
+    }
+    if (blockIdx.x == 0 && tid < 9u * (n & 3u)) {                  // the last n % 4 triangles
+        const float f = tri[(size_t)nq * 36 + tid];
+        const int k = tid % 3;
+        lo[k] = fminf(lo[k], f); hi[k] = fmaxf(hi[k], f);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[k] = fminf(lo[k], __shfl_xor_sync(FULL, lo[k], o));
+            hi[k] = fmaxf(hi[k], __shfl_xor_sync(FULL, hi[k], o));
+        }
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) { s_red[warp][k] = lo[k]; s_red[warp][3 + k] = hi[k]; }
+    }
+    __syncthreads();
+    if (tid < 6) {
+        float r = s_red[0][tid];
+        for (int i = 1; i < 8; i++) r = tid < 3 ? fminf(r, s_red[i][tid]) : fmaxf(r, s_red[i][tid]);
+        if (tid < 3) atomicMin(&enc[tid], enc_float(r)); else atomicMax(&enc[tid], enc_float(r));
+    }
+    grid_barrier(hist + H_BAR, G);
+    // ---- phase 2: Morton keys (R/src/App.cpp:144-156 + R/src/Renderer.cpp:116-136) + the digit histograms of the four sort passes
+    float slo[3], shi[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) { slo[k] = dec_float(__ldcg(enc + k)); shi[k] = dec_float(__ldcg(enc + 3 + k)); }
+    if (blockIdx.x == 0 && tid == 0) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) { hdr->lo[k] = slo[k]; hdr->hi[k] = shi[k]; }
+        st_relaxed(hist + H_EPOCH, epoch + 1u);
+    }
+    {
+        int it = 0;
+        for (uint32_t q0 = blockIdx.x * FRONT_THREADS + (tid & ~31u); q0 < nq; q0 += G * FRONT_THREADS, it++) {
+            const uint32_t q = q0 + lane;
+            const bool valid = q < nq;
+            const uint32_t act = __ballot_sync(FULL, valid);
+            if (valid) {
+                uint32_t code[4];
+                if (KEEP) {
+#pragma unroll
+                    for (int t = 0; t < 4; t++) {
+                        const uint32_t xx = morton_axis_c(s_centre[(it * 12 + t * 3 + 0) * FRONT_THREADS + tid], slo[0], shi[0]);
+                        const uint32_t yy = morton_axis_c(s_centre[(it * 12 + t * 3 + 1) * FRONT_THREADS + tid], slo[1], shi[1]);
+                        const uint32_t zz = morton_axis_c(s_centre[(it * 12 + t * 3 + 2) * FRONT_THREADS + tid], slo[2], shi[2]);
+                        code[t] = xx * 4 + yy * 2 + zz;
+                    }
+                } else {
+                    float v[36];
+                    load_quad(tri, q, v);
+#pragma unroll
+                    for (int t = 0; t < 4; t++) code[t] = morton_of_tri(v + 9 * t, slo, shi);
+                }
+                *reinterpret_cast<uint4*>(keys + (size_t)q * 4) = make_uint4(code[0], code[1], code[2], code[3]);
+#pragma unroll
+                for (int t = 0; t < 4; t++) hist_add(s_hist, code[t], act, lane);
+            }
+        }
+    }
+    if (blockIdx.x == 0 && tid < 32) {                               // the last n % 4 triangles
+        const bool valid = (uint32_t)lane < (n & 3u);
+        const uint32_t act = __ballot_sync(FULL, valid);
+        if (valid) {
+            float t[9];
+#pragma unroll
+            for (int i = 0; i < 9; i++) t[i] = tri[((size_t)nq * 4 + lane) * 9 + i];
+            const uint32_t code = morton_of_tri(t, slo, shi);
+            keys[(size_t)nq * 4 + lane] = code;
+            hist_add(s_hist, code, act, lane);
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < 1024; i += FRONT_THREADS) { uint32_t v = s_hist[i]; if (v) atomicAdd(&hist[H_HIST + i], v); }
+}
+
+// scene-box accumulators and the grid-barrier words in their rest state (once per context)
+int bihrt_build_setup(bihrt_ctx* c) {
+    const uint32_t enc_init[18] = { 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u,
+                                    0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u };
+    BIHRT_CUDA(c, cudaMemcpy(c->d_scenebox_enc, enc_init, sizeof enc_init, cudaMemcpyHostToDevice));
+    BIHRT_CUDA(c, cudaMemset(c->d_hist, 0, 4096 * sizeof(uint32_t)));
+    BIHRT_CUDA(c, cudaFuncSetAttribute(k_front<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FRONT_STAGE_BYTES + FRONT_MAX_KEEP_ITERS * FRONT_KEEP_BYTES_PER_ITER));
+    BIHRT_CUDA(c, cudaFuncSetAttribute(k_front<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FRONT_STAGE_BYTES));
+    return BIHRT_OK;
+}
+
+static int front_launch(bihrt_ctx* c, uint32_t n, uint4* lookback, uint32_t lb_vec4) {
+    const uint32_t nq = n >> 2;
+    const uint32_t G = max(1u, min((uint32_t)(c->sm_count * 2), (nq + FRONT_THREADS - 1) / FRONT_THREADS));
+    const uint32_t iters = (nq + G * FRONT_THREADS - 1) / (G * FRONT_THREADS);
+    const bool keep = iters <= FRONT_MAX_KEEP_ITERS;
+    const size_t smem = FRONT_STAGE_BYTES + (keep ? (size_t)max(1u, iters) * FRONT_KEEP_BYTES_PER_ITER : 0);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(G); cfg.blockDim = dim3(FRONT_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = c->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative; attr[0].val.cooperative = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    const float* tri = c->d_tri_in; uint32_t* enc = c->d_scenebox_enc; uint32_t* keys = c->d_keys[0]; uint32_t* hist = c->d_hist; BihHeader* hdr = c->d_hdr;
+    const uint32_t status0 = (uint32_t)c->opt_debug_trip_watchdog;
+    if (keep) BIHRT_CUDA(c, cudaLaunchKernelEx(&cfg, k_front<true>, tri, n, enc, keys, hist, hdr, lookback, lb_vec4, status0));
+    else      BIHRT_CUDA(c, cudaLaunchKernelEx(&cfg, k_front<false>, tri, n, enc, keys, hist, hdr, lookback, lb_vec4, status0));
+    return BIHRT_OK;
+}
+
+// ------------------------------------------------------------------------------------------
 // One pass of a stable least-significant-digit radix sort, 8-bit digit, single sweep over the data
 // with chained-scan decoupled look-back across tiles (replaces thrust::sequence +
 // thrust::stable_sort_by_key, R/src/Renderer.cpp:436-445).  Stability: a tile is ranked in index
 // order (warp-striped items, per-warp match-any ranking), tiles are ordered by the look-back chain.
 // ------------------------------------------------------------------------------------------
+#ifndef OS_BALLOT
+#define OS_BALLOT 1
+#endif
 #define OS_THREADS 256
 #define OS_ITEMS   16
 #define OS_TILE    (OS_THREADS * OS_ITEMS)      // 4096 keys (32-bit keys; the 64-bit keys of the quality mode use 8 items = 2048 keys)
@@ -279,7 +477,16 @@ __global__ void __launch_bounds__(OS_THREADS) k_onesweep(const K* __restrict__ k
 #pragma unroll
     for (int i = 0; i < OS_ITEMS_; i++) {
         uint32_t d = (uint32_t)(key[i] >> shift) & 255u;
+#if OS_BALLOT
+        uint32_t peers = FULL;
+#pragma unroll
+        for (int b = 0; b < 8; b++) {
+            const uint32_t bit = (d >> b) & 1u;
+            peers &= __ballot_sync(FULL, bit) ^ (bit - 1u);
+        }
+#else
         uint32_t peers = __match_any_sync(FULL, d);
+#endif
         int leader = __ffs(peers) - 1;
         uint32_t old = 0;
         if (lane == leader) { old = s_whist[warp][d]; s_whist[warp][d] = old + __popc(peers); }
@@ -755,11 +962,11 @@ int bihrt_build_launch_q(bihrt_ctx* c) {
     const size_t lb_words = (size_t)8 * os_tiles * 256;
     if (lb_words > c->lookback_q_words || !c->d_keys64[0]) return bihrt_fail(c, BIHRT_ERR_INTERNAL, "quality-mode scratch not allocated");
     const uint32_t lb_vec4 = (uint32_t)((lb_words + 3) / 4);
-    k_init<<<(int)max(1u, min((uint32_t)c->sm_count, (lb_vec4 + 1023u) / 1024u)), 256, 0, st>>>(c->d_hist, c->d_scenebox_enc, c->d_hdr, n,
+    k_init<<<(int)max(1u, min((uint32_t)c->sm_count, (lb_vec4 + 1023u) / 1024u)), 256, 0, st>>>(c->d_hist, c->d_scenebox_enc + ENC_AUX, c->d_hdr, n,
                                                                                       reinterpret_cast<uint4*>(c->d_lookback_q), lb_vec4, (uint32_t)c->opt_debug_trip_watchdog, 1u);
     const int stream_grid = (int)max(1u, min((uint32_t)(c->sm_count * 3), ((n >> 2) + 255) / 256));
-    k_scene_box<<<stream_grid, 256, 0, st>>>(c->d_tri_in, n, c->d_scenebox_enc);
-    k_morton_q<<<(int)max(1u, min((uint32_t)(c->sm_count * 4), (n + 255) / 256)), 256, 0, st>>>(c->d_tri_in, n, c->d_scenebox_enc, c->d_keys64[0], c->d_hist, c->d_hdr);
+    k_scene_box<<<stream_grid, 256, 0, st>>>(c->d_tri_in, n, c->d_scenebox_enc + ENC_AUX);
+    k_morton_q<<<(int)max(1u, min((uint32_t)(c->sm_count * 4), (n + 255) / 256)), 256, 0, st>>>(c->d_tri_in, n, c->d_scenebox_enc + ENC_AUX, c->d_keys64[0], c->d_hist, c->d_hdr);
     int cur = 0;
     for (int pass = 0; pass < 8; pass++) {
         uint32_t* lb = c->d_lookback_q + (size_t)pass * os_tiles * 256;
@@ -797,14 +1004,10 @@ int bihrt_build_launch(bihrt_ctx* c) {
 #define PROF_MARK() do { if (c->opt_profile && pe < BIHRT_PROF_EVENTS) cudaEventRecord(c->prof_ev[pe++], st); } while (0)
     PROF_MARK();
     const uint32_t lb_vec4 = (uint32_t)((lb_words + 3) / 4);        // the buffer is allocated with 16 spare words
-    k_init<<<(int)max(1u, min((uint32_t)c->sm_count, (lb_vec4 + 1023u) / 1024u)), 256, 0, st>>>(c->d_hist, c->d_scenebox_enc, c->d_hdr, n,
-                                                                                      reinterpret_cast<uint4*>(c->d_lookback), lb_vec4, (uint32_t)c->opt_debug_trip_watchdog, 0u);
-    PROF_MARK();   // 1: after init + memsets
-    const int stream_grid = (int)max(1u, min((uint32_t)(c->sm_count * 3), ((n >> 2) + 255) / 256));
-    k_scene_box<<<stream_grid, 256, 0, st>>>(c->d_tri_in, n, c->d_scenebox_enc);
+    PROF_MARK();   // 1
     PROF_MARK();   // 2
-    k_morton<<<stream_grid, 256, 0, st>>>(c->d_tri_in, n, c->d_scenebox_enc, c->d_keys[0], c->d_hist, c->d_hdr);
-    PROF_MARK();   // 3: after morton
+    { int rc = front_launch(c, n, reinterpret_cast<uint4*>(c->d_lookback), lb_vec4); if (rc) return rc; }
+    PROF_MARK();   // 3: after init + scene box + morton (one cooperative launch)
     int cur = 0;
     for (int pass = 0; pass < 4; pass++) {
         uint32_t* lb = c->d_lookback + (size_t)pass * os_tiles * 256;
@@ -835,7 +1038,7 @@ int bihrt_build_launch(bihrt_ctx* c) {
     PROF_MARK();   // 11: after nodes
     PROF_MARK();   // 12: after reorder
     c->prof_count = pe;
-    c->kernel_launches += 11 + launches;   // k_init, k_scene_box, k_morton, 4 x k_onesweep, k_rle_count, k_rle_scan, k_reorder, k_heap_up.., k_nodes
+    c->kernel_launches += 9 + launches;    // k_front, 4 x k_onesweep, k_rle_count, k_rle_scan, k_reorder, k_heap_up.., k_nodes
     BIHRT_CUDA(c, cudaGetLastError());
     return BIHRT_OK;
 }
@@ -860,9 +1063,9 @@ int bihrt_refit_launch(bihrt_ctx* c) {
     uint32_t P = 256;
     while (P < n) P <<= 1;
     const int stream_grid = (int)max(1u, min((uint32_t)(c->sm_count * 3), ((n >> 2) + 255) / 256));
-    k_refit_init<<<1, 32, 0, st>>>(c->d_scenebox_enc);
-    k_scene_box<<<stream_grid, 256, 0, st>>>(c->d_tri_in, n, c->d_scenebox_enc);
-    k_refit_box<<<1, 32, 0, st>>>(c->d_scenebox_enc, c->d_hdr);
+    k_refit_init<<<1, 32, 0, st>>>(c->d_scenebox_enc + ENC_AUX);
+    k_scene_box<<<stream_grid, 256, 0, st>>>(c->d_tri_in, n, c->d_scenebox_enc + ENC_AUX);
+    k_refit_box<<<1, 32, 0, st>>>(c->d_scenebox_enc + ENC_AUX, c->d_hdr);
     k_reorder<false, false><<<(n + 255) / 256, 256, 0, st>>>(c->d_tri_in, c->d_vals[0], c->d_keys[0], n, c->d_tris, c->d_heaps, P, nullptr, nullptr, nullptr);
     int launches = 0;
     for (uint32_t lvl = P >> 8, used = (n + 255) / 256; lvl > 1; lvl >>= 8, used = (used + 255) / 256) {
