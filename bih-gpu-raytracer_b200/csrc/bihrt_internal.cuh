@@ -104,6 +104,8 @@ struct bihrt_ctx {
     uint32_t *d_lookback = nullptr;   // onesweep / RLE decoupled look-back words
     size_t    lookback_words = 0;
     float4   *d_heaps = nullptr;      // implicit min/max heap over the slot boxes: entry e = (lo.xyz, -), (hi.xyz, -) at [2e], [2e+1]; 2P entries
+    unsigned long long *d_xctl = nullptr;  // k_tree: per node, the 64-bit word its two children meet in (tag | far bound of the first to arrive)
+    float4   *d_xbox = nullptr;       // k_tree: per node, the box the first child to arrive leaves for the second (2 x 16 B, tagged)
     uint32_t *d_scenebox_enc = nullptr; // 6 order-preserving encoded floats
 
     // trace
@@ -151,6 +153,7 @@ struct bihrt_ctx {
     int opt_sm_queues = -1; // 1: per-SM work queues (tile locality in L1), 0: one global counter, -1: by launch size
     int64_t kernel_launches = 0;
     int opt_build_graph = 1;            // replay the build as a captured CUDA graph
+    int opt_build_tree = 0;             // 0: upper heap levels + top-down k_nodes; 1: bottom-up k_tree (topology + children boxes in one pass; measured 2.5x slower)
     cudaGraphExec_t build_graph_exec = nullptr; int64_t build_graph_n = -1, build_graph_launches = 0;
     int opt_morton_bits = 30;   // 30: the reference's grid (parity path); 63: quality mode (non-parity)
     int opt_leaf_cap = 4;       // quality mode: a subtree of at most this many triangles becomes one leaf

@@ -12,7 +12,7 @@
 //   k_reorder     per slot: leaf heads -> unique codes + first slot of each leaf (the RLE write, fused);
 //                 gather the triangle, write its 48-byte leaf-ordered record and its AABB as the
 //                 bottom level of an implicit min/max heap of BOXES (32-byte entries, +8 levels per block)   4+36 R + 48+~35 W
-//   k_heap_up     upper heap levels (8 per launch)
+//   k_heap_up     upper heap levels (8 per block, 8 more by the last block to finish: one launch up to 16 M triangles)
 //   k_nodes       per node: Karras range/split search + two heap range queries = the boxes of its two children
 //                 (the clip planes are two components of them); each 64-byte node written once       ~50 R + 64 W
 // Results are bit-identical to the reference algorithm (oracle/bih_oracle.c): the radix tree over the
@@ -243,6 +243,7 @@ __global__ void __launch_bounds__(256) k_morton(const float* __restrict__ tri, u
 // At 1 M triangles: 4 + 11 + 14 us of three launches -> one launch.
 // ------------------------------------------------------------------------------------------
 #define H_BAR    3000      // d_hist words [H_BAR] = arrivals, [H_BAR + 1] = generation of the grid barrier (self-resetting)
+#define H_TREE_TAG 3003     // launches of k_tree so far (bumped by the k_reorder in front of it): the tag of its exchange words
 #define H_EPOCH  3002      // builds started on this context: selects the scene-box accumulator enc[(epoch & 1) * 6 ..]
 #define FRONT_THREADS 256
 #define FRONT_STAGE_BYTES (8 * 288 * 16)              // load_quads_warp staging, one 4608-byte buffer per warp
@@ -271,7 +272,7 @@ __device__ __forceinline__ void grid_barrier(uint32_t* bar, uint32_t G) {
 }
 
 template <bool KEEP>
-__global__ void __launch_bounds__(FRONT_THREADS, 2) k_front(const float* __restrict__ tri, uint32_t n, uint32_t* __restrict__ enc2,
+__global__ void __launch_bounds__(FRONT_THREADS, KEEP ? 2 : 3) k_front(const float* __restrict__ tri, uint32_t n, uint32_t* __restrict__ enc2,
                                                             uint32_t* __restrict__ keys, uint32_t* __restrict__ hist, BihHeader* hdr,
                                                             uint4* __restrict__ lookback, uint32_t lb_vec4, uint32_t status0) {
     extern __shared__ float4 s_dyn[];
@@ -404,9 +405,10 @@ int bihrt_build_setup(bihrt_ctx* c) {
 
 static int front_launch(bihrt_ctx* c, uint32_t n, uint4* lookback, uint32_t lb_vec4) {
     const uint32_t nq = n >> 2;
-    const uint32_t G = max(1u, min((uint32_t)(c->sm_count * 2), (nq + FRONT_THREADS - 1) / FRONT_THREADS));
+    uint32_t G = max(1u, min((uint32_t)(c->sm_count * 2), (nq + FRONT_THREADS - 1) / FRONT_THREADS));
     const uint32_t iters = (nq + G * FRONT_THREADS - 1) / (G * FRONT_THREADS);
     const bool keep = iters <= FRONT_MAX_KEEP_ITERS;
+    if (!keep) G = (uint32_t)(c->sm_count * 3);       // streaming variant: three resident blocks per SM (36 KB of staging each)
     const size_t smem = FRONT_STAGE_BYTES + (keep ? (size_t)max(1u, iters) * FRONT_KEEP_BYTES_PER_ITER : 0);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(G); cfg.blockDim = dim3(FRONT_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = c->stream;
@@ -439,7 +441,7 @@ static int front_launch(bihrt_ctx* c, uint32_t n, uint4* lookback, uint32_t lb_v
 #define LB_MASK       0x3FFFFFFFu
 #define SPIN_LIMIT    (1u << 22)
 
-template <typename K, int ITEMS, bool FIRST>
+template <typename K, int ITEMS, bool FIRST, int LB_BATCH>
 __global__ void __launch_bounds__(OS_THREADS) k_onesweep(const K* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                                                          K* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
                                                          uint32_t n, int pass, uint32_t* __restrict__ hist,
@@ -512,15 +514,29 @@ __global__ void __launch_bounds__(OS_THREADS) k_onesweep(const K* __restrict__ k
         st_relaxed(lb, cnt_real | LB_FLAG_INCL);
     } else {
         st_relaxed(lb, cnt_real | LB_FLAG_AGG);
-        const uint32_t* p = lb - 256;
+        // All tiles of a launch are resident at once and publish their aggregates at about the same time, so a look-back that
+        // reads ONE predecessor per L2 round trip walks ~sqrt(2 * tile) trips (22 at 1 M keys, ~6 us of a 15 us pass).  Read
+        // LB_BATCH predecessors per trip instead (independent loads) and consume them in order: ~sqrt(2 * tile / LB_BATCH) trips.
+        // Measured (1 M keys, per pass): batch 1 / 8 / 16 / 32 = 20.4 / 18.8 / 19.7 / 20.4 us; with several waves of tiles (10 M
+        // keys) the predecessors of a tile have finished long before it starts and the wider reads only cost: 90 / 94 / 107 us.
+        // The host picks 8 for launches of at most one wave, else 1.
+        int t = (int)tile - 1;
         uint32_t spins = 0;
-        for (;;) {
-            uint32_t v = ld_relaxed(p);
-            uint32_t f = v & ~LB_MASK;
-            if (f == 0) { if (++spins > SPIN_LIMIT) { atomicOr(&hdr->status, 1u); break; } continue; }
-            excl += v & LB_MASK;
-            if (f == LB_FLAG_INCL) break;
-            p -= 256;
+        bool done = false;
+        while (!done) {
+            uint32_t v[LB_BATCH];
+#pragma unroll
+            for (int i = 0; i < LB_BATCH; i++) v[i] = (t - i >= 0) ? ld_relaxed(lb - 256 * (size_t)(tile - (uint32_t)(t - i))) : LB_FLAG_INCL;
+#pragma unroll
+            for (int i = 0; i < LB_BATCH; i++) {
+                if (done) break;
+                const uint32_t f = v[i] & ~LB_MASK;
+                if (f == 0) break;                    // not published yet: read again from here
+                excl += v[i] & LB_MASK;
+                t--;
+                if (f == LB_FLAG_INCL) done = true;
+            }
+            if (!done && ++spins > SPIN_LIMIT) { atomicOr(&hdr->status, 1u); break; }
         }
         st_relaxed(lb, (excl + cnt_real) | LB_FLAG_INCL);
     }
@@ -557,13 +573,14 @@ __global__ void __launch_bounds__(OS_THREADS) k_onesweep(const K* __restrict__ k
 // The sorted pairs end in buffer passes & 1.
 int bihrt_sort_pairs_launch(bihrt_ctx* c, uint32_t* keys[2], uint32_t* vals[2], uint32_t n, int passes, uint32_t* hist, uint32_t* lookback, BihHeader* hdr) {
     const uint32_t os_tiles = (n + OS_TILE - 1) / OS_TILE;
+    const bool one_wave = os_tiles <= (uint32_t)c->sm_count * 3u;     // all tiles resident at once: batched look-back (see k_onesweep)
     int cur = 0;
     for (int pass = 0; pass < passes; pass++) {
         uint32_t* lb = lookback + (size_t)pass * os_tiles * 256;
-        if (pass == 0)
-            k_onesweep<uint32_t, OS_ITEMS, true><<<os_tiles, OS_THREADS, 0, c->stream>>>(keys[cur], nullptr, keys[cur ^ 1], vals[cur ^ 1], n, pass, hist, lb, hdr);
-        else
-            k_onesweep<uint32_t, OS_ITEMS, false><<<os_tiles, OS_THREADS, 0, c->stream>>>(keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], n, pass, hist, lb, hdr);
+        if (pass == 0 && one_wave)  k_onesweep<uint32_t, OS_ITEMS, true, 8><<<os_tiles, OS_THREADS, 0, c->stream>>>(keys[cur], nullptr, keys[cur ^ 1], vals[cur ^ 1], n, pass, hist, lb, hdr);
+        else if (pass == 0)         k_onesweep<uint32_t, OS_ITEMS, true, 1><<<os_tiles, OS_THREADS, 0, c->stream>>>(keys[cur], nullptr, keys[cur ^ 1], vals[cur ^ 1], n, pass, hist, lb, hdr);
+        else if (one_wave)          k_onesweep<uint32_t, OS_ITEMS, false, 8><<<os_tiles, OS_THREADS, 0, c->stream>>>(keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], n, pass, hist, lb, hdr);
+        else                        k_onesweep<uint32_t, OS_ITEMS, false, 1><<<os_tiles, OS_THREADS, 0, c->stream>>>(keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], n, pass, hist, lb, hdr);
         cur ^= 1;
     }
     c->kernel_launches += passes;
@@ -613,6 +630,7 @@ __global__ void __launch_bounds__(256) k_rle_count(const uint32_t* __restrict__ 
 }
 
 // exclusive scan of the tile counts in place (one block), Nu and the sentinel first[Nu] = n
+// (folding it into the last block of k_rle_count was measured: 13.3 -> 14.4 us at 1 M triangles, 38 -> 80 us at 10 M)
 __global__ void __launch_bounds__(1024) k_rle_scan(uint32_t* __restrict__ tile_cnt, uint32_t ntiles, uint32_t n,
                                                    uint32_t* __restrict__ first, BihHeader* hdr) {
     __shared__ uint32_t s_w[32];
@@ -637,6 +655,7 @@ __global__ void __launch_bounds__(1024) k_rle_scan(uint32_t* __restrict__ tile_c
     if (threadIdx.x == 0) { const uint32_t nu = s_carry; hdr->nu = nu; first[nu] = n; }
 }
 
+#define H_HEAPCTR 3005     // d_hist word: blocks of k_heap_up that have finished (back at 0 when the kernel ends)
 // ------------------------------------------------------------------------------------------
 // Leaves, tree and clip planes without any inter-thread dependency:
 //   k_reorder     thread per sorted slot: the triangle's AABB becomes the bottom level of six implicit binary
@@ -668,7 +687,7 @@ __device__ __forceinline__ void heap_store(float4* __restrict__ heaps, uint32_t 
 // One block reduces 256 consecutive elements of the level that starts at heap index `in_base` through up to 8 further
 // levels: r[] holds this thread's element on entry (3 maxima, 3 minima).  Five levels inside each warp with shuffles,
 // three more over the 8 warp results: two block barriers instead of sixteen.
-__device__ __forceinline__ void heap_reduce_block(float r[6], float (*s)[8], float4* __restrict__ heaps, uint32_t P, uint32_t in_base) {
+__device__ __forceinline__ void heap_reduce_block(float r[6], float (*s)[8], float4* __restrict__ heaps, uint32_t P, uint32_t in_base, uint32_t blk) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     uint32_t level_base = in_base;
 #pragma unroll
@@ -680,7 +699,7 @@ __device__ __forceinline__ void heap_reduce_block(float r[6], float (*s)[8], flo
             const float y = __shfl_xor_sync(FULL, r[c], 1 << (l - 1));
             r[c] = c < 3 ? fmaxf(r[c], y) : fminf(r[c], y);
         }
-        const uint32_t i = (blockIdx.x * 256u + threadIdx.x) >> l;    // element of this level
+        const uint32_t i = (blk * 256u + threadIdx.x) >> l;    // element of this level
         if ((lane & ((1 << l) - 1)) == 0 && i < level_base) heap_store(heaps, level_base + i, r);
     }
     if (lane == 0) {
@@ -700,7 +719,7 @@ __device__ __forceinline__ void heap_reduce_block(float r[6], float (*s)[8], flo
                 const float y = __shfl_xor_sync(FULL, r[c], 1 << (l - 6));
                 r[c] = c < 3 ? fmaxf(r[c], y) : fminf(r[c], y);
             }
-            const uint32_t i = (blockIdx.x * 8u + lane) >> (l - 5);
+            const uint32_t i = (blk * 8u + lane) >> (l - 5);
             if (lane < 8 && (lane & ((1 << (l - 5)) - 1)) == 0 && i < level_base) heap_store(heaps, level_base + i, r);
         }
     }
@@ -713,10 +732,11 @@ template <bool RLE, bool QUALITY>
 __global__ void __launch_bounds__(256) k_reorder(const float* __restrict__ tri_in, const uint32_t* __restrict__ idx_sorted,
                                                  const uint32_t* __restrict__ keys_sorted, uint32_t n, BihTri* __restrict__ tris,
                                                  float4* __restrict__ heaps, uint32_t P, const uint32_t* __restrict__ tile_off,
-                                                 uint32_t* __restrict__ umc, uint32_t* __restrict__ first) {
+                                                 uint32_t* __restrict__ umc, uint32_t* __restrict__ first, uint32_t* __restrict__ hist) {
     __shared__ float s[6][8];
     __shared__ uint32_t s_w[8];
     const uint32_t j = blockIdx.x * 256u + threadIdx.x;
+    if (j == 0 && hist) hist[H_TREE_TAG] += 1u;      // a fresh tag for the exchange words of the k_tree that follows
     float mn[3] = { INFINITY, INFINITY, INFINITY }, mx[3] = { -INFINITY, -INFINITY, -INFINITY };
     uint32_t key = 0, head = 0;
     if (j < n) {
@@ -749,19 +769,39 @@ __global__ void __launch_bounds__(256) k_reorder(const float* __restrict__ tri_i
         if (head) { umc[k] = key; first[k] = j; }
     }
     float r[6] = { mx[0], mx[1], mx[2], mn[0], mn[1], mn[2] };
-    heap_reduce_block(r, s, heaps, P, P);
+    heap_reduce_block(r, s, heaps, P, P, blockIdx.x);
 }
 
-// 8 more levels above the level of `in_count` used elements that starts at heap index `in_base`
-__global__ void __launch_bounds__(256) k_heap_up(float4* __restrict__ heaps, uint32_t P, uint32_t in_base, uint32_t in_count) {
+// 8 more levels above the level of `in_count` used elements that starts at heap index `in_base`; the last block to finish goes on
+// with the <= 256 elements the launch produced (8 further levels: one launch covers 16 levels, i.e. everything above k_reorder's
+// for up to 16 M triangles)
+__global__ void __launch_bounds__(256) k_heap_up(float4* __restrict__ heaps, uint32_t P, uint32_t in_base, uint32_t in_count, uint32_t* __restrict__ done_ctr) {
     __shared__ float s[6][8];
+    __shared__ uint32_t s_last;
     const uint32_t i = blockIdx.x * 256u + threadIdx.x;
     float r[6] = { -INFINITY, -INFINITY, -INFINITY, INFINITY, INFINITY, INFINITY };
     if (i < in_count) {
         const float4 lo = heaps[2 * (size_t)(in_base + i)], hi = heaps[2 * (size_t)(in_base + i) + 1];
         r[0] = hi.x; r[1] = hi.y; r[2] = hi.z; r[3] = lo.x; r[4] = lo.y; r[5] = lo.z;
     }
-    heap_reduce_block(r, s, heaps, P, in_base);
+    heap_reduce_block(r, s, heaps, P, in_base, blockIdx.x);
+    if (gridDim.x > 256 || (in_base >> 8) <= 1) return;          // the host launches the next step itself / nothing above
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(done_ctr, 1u) == gridDim.x - 1 ? 1u : 0u;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x == 0) *done_ctr = 0u;
+    const uint32_t base2 = in_base >> 8;
+#pragma unroll
+    for (int c = 0; c < 3; c++) { r[c] = -INFINITY; r[3 + c] = INFINITY; }
+    if (threadIdx.x < gridDim.x) {
+        const float4 lo = __ldcg(heaps + 2 * (size_t)(base2 + threadIdx.x)), hi = __ldcg(heaps + 2 * (size_t)(base2 + threadIdx.x) + 1);
+        r[0] = hi.x; r[1] = hi.y; r[2] = hi.z; r[3] = lo.x; r[4] = lo.y; r[5] = lo.z;
+    }
+    __syncthreads();
+    heap_reduce_block(r, s, heaps, P, base2, 0u);
 }
 
 // Boxes of the slot ranges [l0, r0) and [l1, r1) (heap indices at the bottom level), both walked in one loop so that up to
@@ -794,7 +834,10 @@ __device__ __forceinline__ void node_store(BihNode* __restrict__ nd, int axis, u
 #ifndef NODES_BLOCK
 #define NODES_BLOCK 128
 #endif
-__global__ void __launch_bounds__(NODES_BLOCK) k_nodes(const uint32_t* __restrict__ umc, const uint32_t* __restrict__ first,
+#ifndef NODES_MINB
+#define NODES_MINB 1
+#endif
+__global__ void __launch_bounds__(NODES_BLOCK, NODES_MINB) k_nodes(const uint32_t* __restrict__ umc, const uint32_t* __restrict__ first,
                                                BihHeader* hdr, const float4* __restrict__ heaps, uint32_t P,
                                                BihNode* __restrict__ nodes, uint32_t* __restrict__ status_map) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -835,6 +878,129 @@ __global__ void __launch_bounds__(NODES_BLOCK) k_nodes(const uint32_t* __restric
     heap_range_boxes(heaps, sa + P, sm + P, sm + P, sb + P, bl, br);
     node_store(nodes + idx, axis, ref_l, ref_r, bl, br);
     if (idx == 0) hdr->root_axis = (uint32_t)axis;
+}
+
+// ------------------------------------------------------------------------------------------
+// k_tree: topology + children boxes in ONE bottom-up pass, thread per leaf (replaces the upper heap levels and k_nodes on the
+// parity path and in the refit; k_nodes stays as the reference-shaped top-down variant, option build_tree = 0).
+//
+// Why: k_nodes spends ~log(range) dependent loads per node in three searches and two heap range queries, and 32 consecutive
+// nodes always contain one long one -- 14 of 32 lanes busy, 65 us at 1 M triangles.  Bottom-up every node costs O(1):
+//   a thread owns a finished subtree [a, b] of leaves (at first one leaf).  Its parent splits at p = b if the subtree has the
+//   longer common prefix with its right neighbour (delta(b) > delta(a-1); the subtree is then the LEFT child), else at p = a-1.
+//   The two children of p meet in one 64-bit atomic exchange on ctl[p]: the first to arrive leaves its far bound there, deposits
+//   its box in xbox[p] and ends; the second reads both, writes the node record (it knows both children's ranges and boxes) and
+//   climbs on with the union.  No fence anywhere: the bound rides in the atomic itself and every 16-byte half of the deposited
+//   box carries the tag of this launch, so the reader simply waits until both halves show it (aligned 16-byte accesses are
+//   single transactions).  Nothing is cleared between launches either: a stale word never carries the current tag.
+// Node numbering is the reference's (Karras): a LEFT child is the node of its LAST leaf, a right child that of its first leaf,
+// the root is node 0 -- because node i of BuildTree grows away from the neighbour it shares the SHORTER prefix with
+// (R/src/CUDAKernels.cu:616-651).  So the finished subtree [a, b] is node b if delta(b) > delta(a-1), else node a: the same
+// comparison that finds its parent.  Boxes are unions of the same per-slot boxes as the heap queries: bit-identical nodes.
+// ------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ float4 ld_volatile_f4(const float4* p) {
+    float4 v; asm volatile("ld.volatile.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ void st_volatile_f4(float4* p, float4 v) {
+    asm volatile("st.volatile.global.v4.f32 [%0], {%1,%2,%3,%4};" :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// box of the slots [l, r) (bottom-level heap indices): levels 0..8 exist below a k_reorder block, above them walk level 8
+__device__ __forceinline__ void leaf_box(const float4* __restrict__ heaps, uint32_t l, uint32_t r, float b[6]) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) { b[k] = INFINITY; b[3 + k] = -INFINITY; }
+    int level = 0;
+    while (l < r && level < 8) {
+        if (l & 1u) heap_merge(heaps, l++, b);
+        if (r & 1u) heap_merge(heaps, --r, b);
+        l >>= 1; r >>= 1; level++;
+    }
+    for (; l < r; l++) heap_merge(heaps, l, b);
+}
+
+#define TREE_BLOCK 128
+__global__ void __launch_bounds__(TREE_BLOCK) k_tree(const uint32_t* __restrict__ umc, const uint32_t* __restrict__ first,
+                                                     BihHeader* hdr, const float4* __restrict__ heaps, uint32_t P,
+                                                     BihNode* __restrict__ nodes, unsigned long long* __restrict__ ctl,
+                                                     float4* __restrict__ xbox, const uint32_t* __restrict__ hist,
+                                                     uint32_t* __restrict__ status_map) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nu = (int)hdr->nu;
+    if (i == 0) *status_map = hdr->status;      // last kernel of the build: the watchdog word, mirrored into mapped host memory
+    const uint32_t tag = hist[H_TREE_TAG];
+    const float ftag = __uint_as_float(tag);
+    bool alive = i < nu && nu >= 2;
+    int a = i, b = i;
+    uint32_t ka = 0, kb = 0, kl = 0, kr = 0;    // umc[a], umc[b], umc[a-1], umc[b+1]
+    uint32_t ref = 0;                           // reference to the finished subtree [a, b]
+    bool left = false;                          // ... which is the left child of its parent,
+    int p = 0;                                  // ... the node that splits between leaves p and p+1
+    float box[6] = { 0.f, 0.f, 0.f, 0.f, 0.f, 0.f };
+    if (alive) {
+        ka = kb = __ldg(umc + i);
+        int dl = -1, dr = -1;
+        if (i > 0)      { kl = __ldg(umc + i - 1); dl = __clz(kl ^ ka); }
+        if (i < nu - 1) { kr = __ldg(umc + i + 1); dr = __clz(kb ^ kr); }
+        left = dr > dl; p = left ? b : a - 1;
+        const uint32_t s0 = __ldg(first + i), s1 = __ldg(first + i + 1);
+        ref = BIH_REF_LEAFREF(s0);
+        leaf_box(heaps, s0 + P, s1 + P, box);
+    }
+    while (__any_sync(FULL, alive)) {
+        bool second = false;
+        unsigned long long old = 0;
+        if (alive) {
+            old = atomicExch(ctl + p, ((unsigned long long)tag << 32) | (uint32_t)(left ? a : b));
+            second = (uint32_t)(old >> 32) == tag;
+            if (!second) {                      // first to arrive: leave the box and end
+                st_volatile_f4(xbox + 2 * (size_t)p, make_float4(box[0], box[1], box[2], ftag));
+                st_volatile_f4(xbox + 2 * (size_t)p + 1, make_float4(box[3], box[4], box[5], ftag));
+                alive = false;
+            }
+        }
+        __syncwarp();                           // a sibling in this warp has issued its deposit before anyone waits for one
+        if (second) {
+            float4 h0, h1;
+            do { h0 = ld_volatile_f4(xbox + 2 * (size_t)p); } while (__float_as_uint(h0.w) != tag);
+            do { h1 = ld_volatile_f4(xbox + 2 * (size_t)p + 1); } while (__float_as_uint(h1.w) != tag);
+            const float sib[6] = { h0.x, h0.y, h0.z, h1.x, h1.y, h1.z };
+            const int far = (int)(uint32_t)old;
+            const uint32_t ms = left ? kb : kl, ms1 = left ? kr : ka;    // umc[p], umc[p+1]
+            const int axis = (__clz(ms ^ ms1) + 1) % 3;                  // R/src/CUDAKernels.cu:702-706
+            uint32_t ref_l, ref_r;
+            float bl[6], br[6];
+            if (left) {                         // this subtree = [a, p], sibling = [p+1, far]
+                ref_l = ref;
+                b = far; kb = __ldg(umc + b);
+                ref_r = (p + 1 == b) ? BIH_REF_LEAFREF(__ldg(first + p + 1)) : BIH_REF_NODE(p + 1, (__clz(ms1 ^ kb) + 1) % 3);
+#pragma unroll
+                for (int k = 0; k < 6; k++) { bl[k] = box[k]; br[k] = sib[k]; }
+            } else {                            // sibling = [far, p], this subtree = [p+1, b]
+                ref_r = ref;
+                a = far; ka = __ldg(umc + a);
+                ref_l = (a == p) ? BIH_REF_LEAFREF(__ldg(first + a)) : BIH_REF_NODE(p, (__clz(ka ^ ms) + 1) % 3);
+#pragma unroll
+                for (int k = 0; k < 6; k++) { bl[k] = sib[k]; br[k] = box[k]; }
+            }
+            // the node's own index (root = 0, else the end it does not grow from) and its parent, from the same comparison
+            int id = 0;
+            if (a == 0 && b == nu - 1) {
+                hdr->root_axis = (uint32_t)axis;
+                alive = false;
+            } else {
+                int dl = -1, dr = -1;
+                if (a > 0)      { kl = __ldg(umc + a - 1); dl = __clz(kl ^ ka); }
+                if (b < nu - 1) { kr = __ldg(umc + b + 1); dr = __clz(kb ^ kr); }
+                left = dr > dl;
+                id = left ? b : a; p = left ? b : a - 1;
+            }
+            node_store(nodes + id, axis, ref_l, ref_r, bl, br);
+            ref = BIH_REF_NODE(id, axis);
+#pragma unroll
+            for (int k = 0; k < 3; k++) { box[k] = fminf(bl[k], br[k]); box[3 + k] = fmaxf(bl[3 + k], br[3 + k]); }
+        }
+    }
 }
 
 // ==========================================================================================
@@ -971,17 +1137,19 @@ int bihrt_build_launch_q(bihrt_ctx* c) {
     for (int pass = 0; pass < 8; pass++) {
         uint32_t* lb = c->d_lookback_q + (size_t)pass * os_tiles * 256;
         if (pass == 0)
-            k_onesweep<uint64_t, OS_ITEMS64, true><<<os_tiles, OS_THREADS, 0, st>>>(c->d_keys64[cur], nullptr, c->d_keys64[cur ^ 1], c->d_vals[cur ^ 1], n, pass, c->d_hist, lb, c->d_hdr);
+            k_onesweep<uint64_t, OS_ITEMS64, true, 1><<<os_tiles, OS_THREADS, 0, st>>>(c->d_keys64[cur], nullptr, c->d_keys64[cur ^ 1], c->d_vals[cur ^ 1], n, pass, c->d_hist, lb, c->d_hdr);
         else
-            k_onesweep<uint64_t, OS_ITEMS64, false><<<os_tiles, OS_THREADS, 0, st>>>(c->d_keys64[cur], c->d_vals[cur], c->d_keys64[cur ^ 1], c->d_vals[cur ^ 1], n, pass, c->d_hist, lb, c->d_hdr);
+            k_onesweep<uint64_t, OS_ITEMS64, false, 1><<<os_tiles, OS_THREADS, 0, st>>>(c->d_keys64[cur], c->d_vals[cur], c->d_keys64[cur ^ 1], c->d_vals[cur ^ 1], n, pass, c->d_hist, lb, c->d_hdr);
         cur ^= 1;
     }
     uint32_t P = 256;
     while (P < n) P <<= 1;
-    k_reorder<false, true><<<(n + 255) / 256, 256, 0, st>>>(c->d_tri_in, c->d_vals[cur], nullptr, n, c->d_tris, c->d_heaps, P, nullptr, nullptr, nullptr);
+    k_reorder<false, true><<<(n + 255) / 256, 256, 0, st>>>(c->d_tri_in, c->d_vals[cur], nullptr, n, c->d_tris, c->d_heaps, P, nullptr, nullptr, nullptr, nullptr);
     int launches = 0;
-    for (uint32_t lvl = P >> 8, used = (n + 255) / 256; lvl > 1; lvl >>= 8, used = (used + 255) / 256) {
-        k_heap_up<<<(used + 255) / 256, 256, 0, st>>>(c->d_heaps, P, lvl, used);
+    for (uint32_t lvl = P >> 8, used = (n + 255) / 256; lvl > 1; lvl >>= 8, used = (used + 255) / 256) {   // level with `lvl` elements
+        const uint32_t hb = (used + 255) / 256;
+        k_heap_up<<<hb, 256, 0, st>>>(c->d_heaps, P, lvl, used, c->d_hist + H_HEAPCTR);
+        if (hb <= 256 && (lvl >> 8) > 1) { lvl >>= 8; used = hb; }       // its last block has done the next 8 levels as well
         launches++;
     }
     k_nodes_q<<<(n + 127) / 128, 128, 0, st>>>(c->d_keys64[cur], n, (uint32_t)c->opt_leaf_cap, c->d_hdr, c->d_heaps, P, c->d_nodes, c->d_tris, c->d_status_map);
@@ -1009,12 +1177,13 @@ int bihrt_build_launch(bihrt_ctx* c) {
     { int rc = front_launch(c, n, reinterpret_cast<uint4*>(c->d_lookback), lb_vec4); if (rc) return rc; }
     PROF_MARK();   // 3: after init + scene box + morton (one cooperative launch)
     int cur = 0;
+    const bool one_wave = os_tiles <= (uint32_t)c->sm_count * 3u;     // all tiles resident at once: batched look-back (see k_onesweep)
     for (int pass = 0; pass < 4; pass++) {
         uint32_t* lb = c->d_lookback + (size_t)pass * os_tiles * 256;
-        if (pass == 0)
-            k_onesweep<uint32_t, OS_ITEMS, true><<<os_tiles, OS_THREADS, 0, st>>>(c->d_keys[cur], nullptr, c->d_keys[cur ^ 1], c->d_vals[cur ^ 1], n, pass, c->d_hist, lb, c->d_hdr);
-        else
-            k_onesweep<uint32_t, OS_ITEMS, false><<<os_tiles, OS_THREADS, 0, st>>>(c->d_keys[cur], c->d_vals[cur], c->d_keys[cur ^ 1], c->d_vals[cur ^ 1], n, pass, c->d_hist, lb, c->d_hdr);
+        if (pass == 0 && one_wave)  k_onesweep<uint32_t, OS_ITEMS, true, 8><<<os_tiles, OS_THREADS, 0, st>>>(c->d_keys[cur], nullptr, c->d_keys[cur ^ 1], c->d_vals[cur ^ 1], n, pass, c->d_hist, lb, c->d_hdr);
+        else if (pass == 0)         k_onesweep<uint32_t, OS_ITEMS, true, 1><<<os_tiles, OS_THREADS, 0, st>>>(c->d_keys[cur], nullptr, c->d_keys[cur ^ 1], c->d_vals[cur ^ 1], n, pass, c->d_hist, lb, c->d_hdr);
+        else if (one_wave)          k_onesweep<uint32_t, OS_ITEMS, false, 8><<<os_tiles, OS_THREADS, 0, st>>>(c->d_keys[cur], c->d_vals[cur], c->d_keys[cur ^ 1], c->d_vals[cur ^ 1], n, pass, c->d_hist, lb, c->d_hdr);
+        else                        k_onesweep<uint32_t, OS_ITEMS, false, 1><<<os_tiles, OS_THREADS, 0, st>>>(c->d_keys[cur], c->d_vals[cur], c->d_keys[cur ^ 1], c->d_vals[cur ^ 1], n, pass, c->d_hist, lb, c->d_hdr);
         cur ^= 1;
         PROF_MARK();   // 4..7: after each sort pass
     }
@@ -1026,19 +1195,26 @@ int bihrt_build_launch(bihrt_ctx* c) {
     // heaps are padded to a power of two >= n (Nu <= n is only known on the device)
     uint32_t P = 256;
     while (P < n) P <<= 1;
-    k_reorder<true, false><<<(n + 255) / 256, 256, 0, st>>>(c->d_tri_in, c->d_vals[cur], c->d_keys[cur], n, c->d_tris, c->d_heaps, P, tile_cnt, c->d_umc, c->d_first);
+    k_reorder<true, false><<<(n + 255) / 256, 256, 0, st>>>(c->d_tri_in, c->d_vals[cur], c->d_keys[cur], n, c->d_tris, c->d_heaps, P, tile_cnt, c->d_umc, c->d_first, c->d_hist);
     PROF_MARK();   // 9: after reorder + slot boxes + leaves
     int launches = 0;
-    for (uint32_t lvl = P >> 8, used = (n + 255) / 256; lvl > 1; lvl >>= 8, used = (used + 255) / 256) {   // level with `lvl` elements
-        k_heap_up<<<(used + 255) / 256, 256, 0, st>>>(c->d_heaps, P, lvl, used);
-        launches++;
+    if (c->opt_build_tree) {
+        PROF_MARK();   // 10
+        k_tree<<<(n + TREE_BLOCK - 1) / TREE_BLOCK, TREE_BLOCK, 0, st>>>(c->d_umc, c->d_first, c->d_hdr, c->d_heaps, P, c->d_nodes, c->d_xctl, c->d_xbox, c->d_hist, c->d_status_map);
+    } else {
+        for (uint32_t lvl = P >> 8, used = (n + 255) / 256; lvl > 1; lvl >>= 8, used = (used + 255) / 256) {   // level with `lvl` elements
+            const uint32_t hb = (used + 255) / 256;
+            k_heap_up<<<hb, 256, 0, st>>>(c->d_heaps, P, lvl, used, c->d_hist + H_HEAPCTR);
+            if (hb <= 256 && (lvl >> 8) > 1) { lvl >>= 8; used = hb; }       // its last block has done the next 8 levels as well
+            launches++;
+        }
+        PROF_MARK();   // 10: after upper heap levels
+        k_nodes<<<(n + NODES_BLOCK - 1) / NODES_BLOCK, NODES_BLOCK, 0, st>>>(c->d_umc, c->d_first, c->d_hdr, c->d_heaps, P, c->d_nodes, c->d_status_map);
     }
-    PROF_MARK();   // 10: after upper heap levels
-    k_nodes<<<(n + NODES_BLOCK - 1) / NODES_BLOCK, NODES_BLOCK, 0, st>>>(c->d_umc, c->d_first, c->d_hdr, c->d_heaps, P, c->d_nodes, c->d_status_map);
     PROF_MARK();   // 11: after nodes
     PROF_MARK();   // 12: after reorder
     c->prof_count = pe;
-    c->kernel_launches += 9 + launches;    // k_front, 4 x k_onesweep, k_rle_count, k_rle_scan, k_reorder, k_heap_up.., k_nodes
+    c->kernel_launches += 9 + launches;    // k_front, 4 x k_onesweep, k_rle_count, k_rle_scan, k_reorder, k_heap_up.., k_nodes (or k_tree)
     BIHRT_CUDA(c, cudaGetLastError());
     return BIHRT_OK;
 }
@@ -1066,13 +1242,19 @@ int bihrt_refit_launch(bihrt_ctx* c) {
     k_refit_init<<<1, 32, 0, st>>>(c->d_scenebox_enc + ENC_AUX);
     k_scene_box<<<stream_grid, 256, 0, st>>>(c->d_tri_in, n, c->d_scenebox_enc + ENC_AUX);
     k_refit_box<<<1, 32, 0, st>>>(c->d_scenebox_enc + ENC_AUX, c->d_hdr);
-    k_reorder<false, false><<<(n + 255) / 256, 256, 0, st>>>(c->d_tri_in, c->d_vals[0], c->d_keys[0], n, c->d_tris, c->d_heaps, P, nullptr, nullptr, nullptr);
+    k_reorder<false, false><<<(n + 255) / 256, 256, 0, st>>>(c->d_tri_in, c->d_vals[0], c->d_keys[0], n, c->d_tris, c->d_heaps, P, nullptr, nullptr, nullptr, c->d_hist);
     int launches = 0;
-    for (uint32_t lvl = P >> 8, used = (n + 255) / 256; lvl > 1; lvl >>= 8, used = (used + 255) / 256) {
-        k_heap_up<<<(used + 255) / 256, 256, 0, st>>>(c->d_heaps, P, lvl, used);
-        launches++;
+    if (c->opt_build_tree) {
+        k_tree<<<(n + TREE_BLOCK - 1) / TREE_BLOCK, TREE_BLOCK, 0, st>>>(c->d_umc, c->d_first, c->d_hdr, c->d_heaps, P, c->d_nodes, c->d_xctl, c->d_xbox, c->d_hist, c->d_status_map);
+    } else {
+        for (uint32_t lvl = P >> 8, used = (n + 255) / 256; lvl > 1; lvl >>= 8, used = (used + 255) / 256) {   // level with `lvl` elements
+            const uint32_t hb = (used + 255) / 256;
+            k_heap_up<<<hb, 256, 0, st>>>(c->d_heaps, P, lvl, used, c->d_hist + H_HEAPCTR);
+            if (hb <= 256 && (lvl >> 8) > 1) { lvl >>= 8; used = hb; }       // its last block has done the next 8 levels as well
+            launches++;
+        }
+        k_nodes<<<(n + NODES_BLOCK - 1) / NODES_BLOCK, NODES_BLOCK, 0, st>>>(c->d_umc, c->d_first, c->d_hdr, c->d_heaps, P, c->d_nodes, c->d_status_map);
     }
-    k_nodes<<<(n + NODES_BLOCK - 1) / NODES_BLOCK, NODES_BLOCK, 0, st>>>(c->d_umc, c->d_first, c->d_hdr, c->d_heaps, P, c->d_nodes, c->d_status_map);
     c->kernel_launches += 5 + launches;
     BIHRT_CUDA(c, cudaGetLastError());
     return BIHRT_OK;

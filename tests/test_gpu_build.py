@@ -141,3 +141,40 @@ def test_refit_keeps_hits_correct(renderer, scenes, oracle):
     renderer.build()                                                        # a full rebuild is the parity path again
     from conftest import assert_view_equals_oracle
     assert_view_equals_oracle(renderer.reference_view(), ob)
+
+
+@pytest.mark.parametrize("name", ["cornell", "sphere187", "atrium", "duplicates", "flat", "soup8193", "single", "two"])
+def test_bottom_up_tree_option_is_bit_exact(renderer, scenes, oracle, name):
+    """Option build_tree = 1: topology + children boxes in one bottom-up pass (k_tree; measured slower and left off).
+    Same node numbering, references, clip planes and children boxes as the top-down path, rebuilt twice (the exchange words are
+    never cleared between launches) and through a refit."""
+    tri = {
+        "cornell": lambda: scenes.cornell_box(),
+        "sphere187": lambda: scenes.displaced_sphere(187),
+        "atrium": lambda: scenes.atrium(),
+        "duplicates": lambda: np.repeat(scenes.dodecahedron(), 5, axis=0),
+        "flat": lambda: scenes.quad_grid([0, 0, 0], [1, 0, 0], [0, 1, 0], 40, 30),
+        "soup8193": lambda: scenes.random_soup(8193, size=0.1, seed=5),
+        "single": lambda: np.tile(np.array([[0, 0, 0, 1, 0, 0, 0, 1, 0]], np.float32), (7, 1)),
+        "two": lambda: scenes.random_soup(2, size=0.1, seed=2),
+    }[name]()
+    import torch
+    from bihrt import multi
+
+    def blob():
+        ptr, nbytes = renderer.bih_region(len(tri))
+        renderer.sync()
+        return torch.as_tensor(multi._CudaView(ptr, (nbytes,), "|u1"), device="cuda:%d" % renderer.device).cpu().numpy()
+
+    renderer.load_models(tri).build()
+    blob_ref = blob()
+    renderer.set_option("build_tree", 1)
+    try:
+        for _ in range(2):
+            renderer.build()
+            assert_view_equals_oracle(renderer.reference_view(), oracle.Bih(tri))
+            assert np.array_equal(blob(), blob_ref)          # header, 64-byte nodes (children boxes), triangle records
+        renderer.refit()
+        assert np.array_equal(blob(), blob_ref)
+    finally:
+        renderer.set_option("build_tree", 0)
