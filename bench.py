@@ -453,12 +453,15 @@ def run_ours(args, rank, world, local_rank):
             else:
                 r.framebuffer(out=host_fb[0])               # D2H, pinned; synchronises
 
+    upload_mode = os.environ.get("BIHRT_BENCH_E2E_UPLOAD", "one")
+
     def e2e_pipelined(k_frames):
         """k_frames frames through the pipeline; returns this rank's ms (events on the launching stream, the last
         frame's download included)."""
         fb2 = torch.as_tensor(multi._CudaView(peer_ptr, (2, H, W), "<i4"), device=dev) if rank == 0 else None
         ev_in = [torch.cuda.Event() for _ in range(2)]
         ev_free = [torch.cuda.Event() for _ in range(2)]
+
         ev_rend = [torch.cuda.Event() for _ in range(2)]
         ev_out = [None, None]
         with torch.cuda.stream(stream):
@@ -467,35 +470,52 @@ def run_ours(args, rank, world, local_rank):
             e0.record(stream)
             copy_in.wait_stream(stream)
             copy_out.wait_stream(stream)
+            dbg = os.environ.get("BIHRT_BENCH_E2E_DEBUG") and k_frames > 4
+            marks, host_t = [], []
             for k in range(k_frames):
                 b = k & 1
-                # the frame's vertices cross PCIe ONCE: rank k % N uploads them over its own link (so every link carries one
-                # upload every N frames and rank 0's link is left to the framebuffer download) and hands them to the others
-                # over NVLink -- one broadcast of 36 MB on the launching stream
-                if rank == k % world:
+                if dbg:
+                    host_t.append(time.perf_counter())
+                    m = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+                    marks.append(m); m[0].record(stream)
+                # "one" (default): the frame's vertices cross PCIe ONCE -- rank k % N uploads them over its own link (every link
+                # carries one upload every N frames; rank 0's is left to the framebuffer download) and hands them to the others with one
+                # 36 MB NCCL broadcast over NVLink on the launching stream (0.24 ms of the 8-GPU frame).  "each": every rank uploads
+                # its own copy on its copy stream.  Measured at 8 GPUs (BIHRT_BENCH_E2E_DEBUG=1): the broadcast disappears from the
+                # launching stream, but DMA traffic next to the kernels slows them -- build 0.20 -> 0.32 ms, trace 1.47 -> 1.54 ms,
+                # rank 0 (download + upload) build 0.64 ms -- and the frame takes 2.26-2.36 ms against 2.11-2.21 with "one".
+                # Also measured: the broadcast issued a frame ahead on its own stream and communicator.  The receivers' NCCL kernels
+                # then sit on a few SMs until the sender's trace kernel has drained, and the build's cooperative k_front cannot
+                # become co-resident next to them: the frame period DOUBLES (2 GPUs: 6.0 -> 11.8 ms).  Left as it was.
+                if upload_mode == "each" or rank == k % world:
                     with torch.cuda.stream(copy_in):
                         if k >= 2:
                             copy_in.wait_event(ev_free[b])       # frame k-2's build input has been consumed
                         dev_tri[b].copy_(pinned_tri, non_blocking=True)      # H2D on the copy stream
                         ev_in[b].record(copy_in)
                     stream.wait_event(ev_in[b])
-                if world > 1:
+                if world > 1 and upload_mode != "each":
                     dist.broadcast(dev_tri[b], src=k % world)
                 r.update_vertices(dev_tri[b])                    # device -> the context's input array (36 MB D2D)
                 ev_free[b].record(stream)
+                if dbg: marks[-1][1].record(stream)
                 r.build()
+                if dbg: marks[-1][2].record(stream)
                 render_my_share(b)
+                if dbg: marks[-1][3].record(stream)
                 # peers store into half b of rank 0's buffer: rank 0 joins the barrier of frame k only once its download of
                 # frame k-1 is done, so when a peer passes this barrier the half it writes NEXT frame is free
                 if rank == 0 and ev_out[b ^ 1] is not None:
                     stream.wait_event(ev_out[b ^ 1])
                 if world > 1:
                     multi.frame_barrier(dist, token)
+                if dbg: marks[-1][4].record(stream)
                 if rank == 0:
                     ev_rend[b].record(stream)
                     with torch.cuda.stream(copy_out):
                         copy_out.wait_event(ev_rend[b])
-                        host_fb[b].copy_(fb2[b], non_blocking=True)      # D2H on the copy stream
+                        if not os.environ.get("BIHRT_BENCH_E2E_NO_D2H"):
+                            host_fb[b].copy_(fb2[b], non_blocking=True)      # D2H on the copy stream
                         ev_out[b] = torch.cuda.Event()
                         ev_out[b].record(copy_out)
             if rank == 0:
@@ -503,7 +523,12 @@ def run_ours(args, rank, world, local_rank):
                     if e is not None:
                         stream.wait_event(e)
             e1.record(stream)
+            host_end = time.perf_counter()
             e1.synchronize()
+            if dbg:
+                seg = np.array([[m[i].elapsed_time(m[i + 1]) for i in range(4)] + [marks[j][0].elapsed_time(marks[j + 1][0]) if j + 1 < len(marks) else float('nan')] for j, m in enumerate(marks)])
+                log("rank %d e2e pipeline (ms, median over frames): wait+upload->input %.3f  build %.3f  trace %.3f  barrier(+download wait) %.3f  | frame period %.3f | host enqueue per frame %.3f" % (
+                    (rank,) + tuple(np.nanmedian(seg, axis=0)) + ((host_end - host_t[0]) / k_frames * 1e3,)))
             return e0.elapsed_time(e1)
 
     e2e_steps = max(2, min(args.steps, 5))
@@ -687,14 +712,16 @@ def run_ours(args, rank, world, local_rank):
                "build_ms_per_mtri": build_ms / (n_tri / 1e6), "build_ms": build_ms,
                "build_roofline": {"bound": "hbm", "algorithmic_bytes_per_triangle": 320, "achieved": n_tri * 320 / (build_ms * 1e-3) / 1e9,
                                   "peak": peak, "unit": "GB/s", "frac": n_tri * 320 / (build_ms * 1e-3) / 1e9 / peak},
-               "e2e": {"value": e2e_val, "unit": "Mrays/s", "h2d_bytes_per_step": n_tri * 36 if can_pipe else n_tri * 36 * world, "d2h_bytes_per_step": W * H * 4,
+               "e2e": {"value": e2e_val, "unit": "Mrays/s", "h2d_bytes_per_step": n_tri * 36 if (can_pipe and upload_mode == "one") else n_tri * 36 * world, "d2h_bytes_per_step": W * H * 4,
                        "ms_per_step": ms_e2e, "frames_timed": e2e_frames, "frame_crc32": e2e_crc,
                        "serial_value": rays_total / (ms_e2e_serial * 1e-3) / 1e6, "serial_ms_per_step": ms_e2e_serial,
-                       "what": ("per frame: vertices H2D from pinned host memory (36 MB, by rank frame %% %d over its own PCIe link%s) + bihrt_build on every rank (local, "
+                       "upload": upload_mode if can_pipe else "each",
+                       "what": ("per frame: vertices H2D from pinned host memory (36 MB%s) + bihrt_build on every rank (local, "
                                 "deterministic: identical trees, no BIH broadcast) + every rank's share of the frame stored into rank 0's framebuffer%s; rank 0: framebuffer D2H to "
                                 "pinned memory.  Pipelined frame loop: the upload of frame k+1 and the download of frame k-1 run on copy streams while frame k is traced (value); "
                                 "serial_value = every rank uploads its own copy, nothing overlapped" % (
-                                    world, ", then one NVLink broadcast" if world > 1 else "", " over NVLink + frame barrier" if world > 1 else "")) if can_pipe else
+                                    (", by every rank over its own PCIe link" if upload_mode == "each" else ", by rank frame %% %d over its own PCIe link, then one NVLink broadcast" % world) if world > 1 else "",
+                                    " over NVLink + frame barrier" if world > 1 else "")) if can_pipe else
                                "vertices H2D (pinned) + bihrt_build + render + framebuffer reduce + D2H (pinned), per frame, serial"},
                "gpu_launches": int(launches), "clocks": clocks}
         if animated:
