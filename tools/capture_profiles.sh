@@ -12,7 +12,7 @@ ncu --set full --clock-control none --import-source on -k regex:k_trace -s 1 -c 
     python tools/prof_one.py --w 3840 --h 2160 --spp 16 --reps 2 > gpurun_out/ncu2.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_trace -s 1 -c 1 -f -o gpurun_out/prof_trace_1080p1 \
     python tools/prof_one.py --spp 1 --reps 2 > gpurun_out/ncu3.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"k_(init|scene_box|morton|onesweep|rle|reorder|heap_up|nodes)" -c 14 -f -o gpurun_out/prof_build \
+ncu --set full --clock-control none --import-source on -k regex:"k_(front|init|scene_box|morton|onesweep|rle|reorder|heap_up|nodes)" -c 10 -f -o gpurun_out/prof_build \
     python tools/prof_one.py --spp 1 --reps 1 > gpurun_out/ncu4.log 2>&1
 python tools/prof_one.py --scene 10m --w 3840 --h 2160 --spp 16 --reps 2 > gpurun_out/plain5.log 2>&1 || exit 1
 ncu --set full --clock-control none --import-source on -k regex:k_trace -s 1 -c 1 -f -o gpurun_out/prof_trace_4k16_10m \
