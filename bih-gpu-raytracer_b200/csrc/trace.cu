@@ -70,6 +70,9 @@
 #ifndef TRACE_TOP_NODES
 #define TRACE_TOP_NODES 0
 #endif
+#ifndef TRACE_LDG256
+#define TRACE_LDG256 1
+#endif
 #define TOP_FLAG 0x40000000u
 #define BOX_EPS 2.384185791015625e-07f      /* 2^-22: relative (and, times |o/d|, absolute) margin of the box tests */
 
@@ -492,7 +495,23 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
                 if (cur & TOP_FLAG) { const float4* tp4 = s_top + ((cur & ~TOP_FLAG) >> 2) * 4; nd = tp4[0]; b0 = tp4[1]; b1 = tp4[2]; b2 = tp4[3]; }
                 else { nd = __ldg(np); b0 = __ldg(np + 1); b1 = __ldg(np + 2); b2 = __ldg(np + 3); }
 #else
+#if TRACE_LDG256
+                // Ray lists (MODE 0) fetch the 64-byte node as TWO 256-bit read-only loads (LDG.E.256, new on sm_100) instead of
+                // four 128-bit ones.  Measured (B200, Mrays/s, 128-bit -> 256-bit): diffuse bounce list on the atrium 2157 -> 2304
+                // (there every lane fetches its own node and the L1 tag stage is the busiest unit, 88 %), 1 M triangles 1080p x 1
+                // spp 6045 -> 6230, 10 M 3282 -> 3403; but coherent packets lose -- 4K x 16 spp 12014 -> 11833, atrium x 4 spp
+                // 6613 -> 6475 (the 8-register alignment of the destination costs two spills in a 64-register kernel).  So the
+                // camera modes keep the 128-bit loads.
+                float4 nd, b0, b1, b2;
+                if (MODE == 0) {
+                    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                        : "=f"(nd.x), "=f"(nd.y), "=f"(nd.z), "=f"(nd.w), "=f"(b0.x), "=f"(b0.y), "=f"(b0.z), "=f"(b0.w) : "l"(np));
+                    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                        : "=f"(b1.x), "=f"(b1.y), "=f"(b1.z), "=f"(b1.w), "=f"(b2.x), "=f"(b2.y), "=f"(b2.z), "=f"(b2.w) : "l"(np + 2));
+                } else { nd = __ldg(np); b0 = __ldg(np + 1); b1 = __ldg(np + 2); b2 = __ldg(np + 3); }
+#else
                 const float4 nd = __ldg(np), b0 = __ldg(np + 1), b1 = __ldg(np + 2), b2 = __ldg(np + 3);
+#endif
 #endif
                 if (COUNTED) { nnodes++; const uint32_t am = __activemask(); wnode += (lane == __ffs(am) - 1); }
                 const uint32_t rl = __float_as_uint(nd.z), rr = __float_as_uint(nd.w);
