@@ -48,7 +48,9 @@ __device__ __forceinline__ uint32_t block_excl_scan_256(uint32_t v, uint32_t* s_
 #define STAMP(k)
 #endif
 
-#if VARIANT == 1
+#if VARIANT == 2
+#include "sortlab_hybrid.cuh"
+#elif VARIANT == 1
 #include "sortlab_coop.cuh"
 #else
 #include "sortlab_kernels.cuh"
