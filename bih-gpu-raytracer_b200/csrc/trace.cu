@@ -533,6 +533,8 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
                 const float fLo = fmaxf(fMin, neg ? bnL : bnR), fHi = fminf(pMax, neg ? bfL : bfR);
                 const bool go_near = (Q || rMin < tn) && (nLo <= nHi);   // reference's strict test (:292) + closed tight interval
                 const bool go_far = (fLo <= fHi);
+                // (the four cases as SELECTS instead of branch targets were measured: 4K x 16 spp 11997 -> 11259 Mrays/s, atrium -9 %:
+                // coherent lanes mostly agree on the case, and the selects cost every lane every time)
                 if (go_near && go_far) {
                     // near before far, except a far LEAF next to a near NODE is tested first (:344-349)
                     if ((int)refn >= 0 && (int)reff < 0) {

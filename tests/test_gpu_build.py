@@ -178,3 +178,25 @@ def test_bottom_up_tree_option_is_bit_exact(renderer, scenes, oracle, name):
         assert np.array_equal(blob(), blob_ref)
     finally:
         renderer.set_option("build_tree", 0)
+
+
+def test_builds_alternate_cleanly_between_parity_quality_and_refit(renderer, scenes, oracle):
+    """k_front alternates between two scene-box accumulators (nothing is cleared before a build); the quality mode and the
+    refit use a third one.  Any interleaving must give the reference's tree again, on a scene whose box CHANGES between builds."""
+    a, b = scenes.displaced_sphere(48, phase=0.0), scenes.displaced_sphere(48, phase=0.9) * np.float32(1.7)
+    oa, ob = oracle.Bih(a), oracle.Bih(b)
+    renderer.load_models(a).build()
+    assert_view_equals_oracle(renderer.reference_view(), oa)
+    try:
+        renderer.set_option("morton_bits", 63)
+        renderer.build()                                    # quality build of a (own accumulator)
+        renderer.set_option("morton_bits", 30)
+        renderer.update_vertices(b).build()                 # parity build of the larger scene
+        assert_view_equals_oracle(renderer.reference_view(), ob)
+        renderer.update_vertices(a).refit()                 # refit back to a (non-parity tree, own accumulator) ...
+        renderer.build()                                    # ... and two parity builds in a row
+        assert_view_equals_oracle(renderer.reference_view(), oa)
+        renderer.update_vertices(b).build()
+        assert_view_equals_oracle(renderer.reference_view(), ob)
+    finally:
+        renderer.set_option("morton_bits", 30)
