@@ -191,12 +191,15 @@ def test_builds_alternate_cleanly_between_parity_quality_and_refit(renderer, sce
         renderer.set_option("morton_bits", 63)
         renderer.build()                                    # quality build of a (own accumulator)
         renderer.set_option("morton_bits", 30)
-        renderer.update_vertices(b).build()                 # parity build of the larger scene
+        renderer.update_vertices(b)
+        renderer.build()                                    # parity build of the larger scene
         assert_view_equals_oracle(renderer.reference_view(), ob)
-        renderer.update_vertices(a).refit()                 # refit back to a (non-parity tree, own accumulator) ...
+        renderer.update_vertices(a)
+        renderer.refit()                                    # refit back to a (non-parity tree, own accumulator) ...
         renderer.build()                                    # ... and two parity builds in a row
         assert_view_equals_oracle(renderer.reference_view(), oa)
-        renderer.update_vertices(b).build()
+        renderer.update_vertices(b)
+        renderer.build()
         assert_view_equals_oracle(renderer.reference_view(), ob)
     finally:
         renderer.set_option("morton_bits", 30)
