@@ -434,6 +434,18 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
                 if (tzmin > tMin) tMin = tzmin;
                 if (tzmax < tMax) tMax = tzmax;
                 if (in) {
+                    // ... and the rounding of the FMA itself is a RELATIVE error of 2^-24 in t.  A box test can only change its
+                    // outcome when the distance in question lies at an end of the ray's interval, i.e. inside the scene box:
+                    // 2^-22 x the larger end of the scene interval bounds four times that error for every distance that
+                    // matters, and makes the margin ONE constant per ray (one add per bound instead of an add and an FMA)
+                    const float tabs = fmaxf(fabsf(tMin), fabsf(tMax));
+                    bpad = __fmaf_rn(BOX_EPS, tabs <= FLT_MAX ? tabs : FLT_MAX, bpad);
+                    // a zero direction component: fma(plane, inf, -(o * inf)) is inf - inf = NaN or a signed infinity depending on
+                    // the signs of plane and origin, never a distance.  The box tests take NaN as 1 / d for that axis, so both its
+                    // plane distances are NaN and the NaN-dropping min / max leave the axis out (no constraint: conservative).  The
+                    // plane logic of the BIH proper keeps the reference's infinity (it reads 1 / d from shared memory).
+                    const float qnan = __uint_as_float(0x7fc00000u);
+                    ix = fabsf(ix) <= FLT_MAX ? ix : qnan; iy = fabsf(iy) <= FLT_MAX ? iy : qnan; iz = fabsf(iz) <= FLT_MAX ? iz : qnan;
                     rMin = tMin; pMin = fmaxf(tMin, 0.f); pMax = (MODE == 0 && a.any_hit) ? fminf(tMax, h.t) : tMax;
                     // Nu == 1: no internal node; the single leaf starts at slot 0 (and must not be
                     // interval-pruned: the reference tests it unconditionally once the box is hit)
@@ -466,8 +478,8 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
             const float az0 = __fmaf_rn((lz), iz, nz), az1 = __fmaf_rn((hz), iz, nz);                       \
             const float n_ = fmaxf(fmaxf(fminf(ax0, ax1), fminf(ay0, ay1)), fminf(az0, az1));               \
             const float f_ = fminf(fminf(fmaxf(ax0, ax1), fmaxf(ay0, ay1)), fmaxf(az0, az1));               \
-            (bn) = __fmaf_rn(-fabsf(n_), BOX_EPS, __fsub_rn(n_, bpad));                                     \
-            (bf) = __fmaf_rn(fabsf(f_), BOX_EPS, __fadd_rn(f_, bpad));                                      \
+            (bn) = __fsub_rn(n_, bpad);                                                                     \
+            (bf) = __fadd_rn(f_, bpad);                                                                     \
         } while (0)
 #define POP_VALID()                                                                                         \
         do {                                                                                                \

@@ -519,24 +519,31 @@ static void traverse_proper(const orc_scene* s, const orc_ray* r, orc_hit* rec, 
 /* plane distance as ONE fused multiply-add: t = fma(plane, 1/d, -(o/d)).  The rounding of o/d is an absolute error of
  * 2^-24 |o/d| in t, so every box interval is widened by pad = 2^-22 x the largest finite |o/d| of the ray, and by 2^-22
  * relative for the rounding of the FMA itself. */
-typedef struct { float n[3], pad; } orc_boxray;
-static inline void make_boxray(orc_boxray* q, const orc_ray* r) {
+typedef struct { float inv[3], n[3], pad; } orc_boxray;
+static inline void make_boxray(orc_boxray* q, const orc_ray* r, float sMin, float sMax) {
     float m = 0.0f;
     for (int k = 0; k < 3; k++) {
         q->n[k] = -(r->o[k] * r->inv[k]);
         float a = fabsf(q->n[k]);
         m = dev_fmaxf(m, a <= FLT_MAX ? a : 0.0f);
+        /* a zero direction component: fma(plane, inf, -(o * inf)) is NaN or a signed infinity depending on signs, never a
+         * distance; NaN as 1 / d makes both plane distances of the axis NaN and the NaN-dropping min / max leave it out */
+        q->inv[k] = fabsf(r->inv[k]) <= FLT_MAX ? r->inv[k] : NAN;
     }
-    q->pad = BOX_EPS * m;
+    /* + 2^-22 x the larger end of the ray's interval inside the scene box: the relative rounding error of the FMA, bounded once
+     * per ray for every distance that can decide a test (those at an end of the current interval) */
+    float tabs = dev_fmaxf(fabsf(sMin), fabsf(sMax));
+    q->pad = fmaf(BOX_EPS, tabs <= FLT_MAX ? tabs : FLT_MAX, BOX_EPS * m);
 }
 static inline void box_slab(const float* b /* lo.xyz hi.xyz */, const orc_ray* r, const orc_boxray* q, float* bn, float* bf) {
-    float ax0 = fmaf(b[0], r->inv[0], q->n[0]), ax1 = fmaf(b[3], r->inv[0], q->n[0]);
-    float ay0 = fmaf(b[1], r->inv[1], q->n[1]), ay1 = fmaf(b[4], r->inv[1], q->n[1]);
-    float az0 = fmaf(b[2], r->inv[2], q->n[2]), az1 = fmaf(b[5], r->inv[2], q->n[2]);
+    (void)r;
+    float ax0 = fmaf(b[0], q->inv[0], q->n[0]), ax1 = fmaf(b[3], q->inv[0], q->n[0]);
+    float ay0 = fmaf(b[1], q->inv[1], q->n[1]), ay1 = fmaf(b[4], q->inv[1], q->n[1]);
+    float az0 = fmaf(b[2], q->inv[2], q->n[2]), az1 = fmaf(b[5], q->inv[2], q->n[2]);
     float n_ = dev_fmaxf(dev_fmaxf(dev_fminf(ax0, ax1), dev_fminf(ay0, ay1)), dev_fminf(az0, az1));
     float f_ = dev_fminf(dev_fminf(dev_fmaxf(ax0, ax1), dev_fmaxf(ay0, ay1)), dev_fmaxf(az0, az1));
-    *bn = fmaf(-fabsf(n_), BOX_EPS, n_ - q->pad);
-    *bf = fmaf(fabsf(f_), BOX_EPS, f_ + q->pad);
+    *bn = n_ - q->pad;
+    *bf = f_ + q->pad;
 }
 
 static void traverse_box(const orc_scene* s, const float* cbox /* 12 floats per node: left box, right box */,
@@ -550,7 +557,7 @@ static void traverse_box(const orc_scene* s, const float* cbox /* 12 floats per 
     int sp = 0;
     int cur = 0;
     orc_boxray q;
-    make_boxray(&q, r);
+    make_boxray(&q, r, rMin, sMax);
     for (;;) {
         int next = 0;
         if (pMin <= dev_fminf(pMax, (float)rec->t)) {

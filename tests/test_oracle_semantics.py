@@ -132,3 +132,31 @@ def test_tool_ray_generator_matches_the_oracle(oracle, scenes):
                       (scenes.atrium_camera(64 / 36), 64, 36)):
         np.testing.assert_array_equal(scenes.camera_rays(cam, w, h), oracle.camera_rays(cam, w, h))
 
+
+
+def test_box_mode_equals_reference_on_degenerate_rays(oracle, scenes):
+    """Zero direction components (1/0 = inf), origins on grid planes and on the scene box, diagonal directions: the children
+    boxes of the shipped traversal (mode 'box') must never cull what the literal TraverseTree ('ref') enters.  With 1/d = inf the
+    fused plane distance fma(plane, inf, -(o * inf)) is NaN or a signed infinity depending on signs, never a distance: the box
+    tests take NaN as 1/d for such an axis and leave it out (regression test: a margin without that rule lost 30 % of these hits)."""
+    tri = np.concatenate([scenes.cornell_box(), scenes.displaced_sphere(24) * 0.3])
+    ob = oracle.Bih(tri)
+    rng = np.random.default_rng(7)
+    n = 20000
+    o = rng.uniform(-1.2, 1.2, (n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    which = rng.integers(0, 7, n)
+    d[which == 0, 0] = 0.0
+    d[which == 1, 1] = 0.0
+    d[which == 2, 2] = 0.0
+    d[which == 3, :2] = 0.0
+    o[which == 4] = np.round(o[which == 4] * 4) / 4
+    d[which == 5] = np.sign(d[which == 5])
+    o[which == 6, 0] = -1.0
+    d[(which == 3) & (d[:, 2] == 0), 2] = 1.0
+    rays = np.concatenate([o, d], 1).astype(np.float32)
+    t0, s0, p0 = ob.trace(rays, "ref")
+    t1, s1, p1 = ob.trace(rays, "box")
+    assert (s0 >= 0).sum() > 1000
+    np.testing.assert_array_equal(s0, s1)
+    np.testing.assert_array_equal(t0, t1)
