@@ -74,7 +74,7 @@
 #define TRACE_LDG256 1
 #endif
 #define TOP_FLAG 0x40000000u
-#define BOX_EPS 2.384185791015625e-07f      /* 2^-22: relative (and, times |o/d|, absolute) margin of the box tests */
+#define BOX_EPS 2.384185791015625e-07f      /* 2^-22: the box tests' margin is this times (largest finite |o/d| + larger end of the ray's scene interval), one constant per ray */
 
 // (double)det < 0.000001 (R/src/CUDAKernels.cu:28)  <=>  det < 0x358637be as binary32
 #define DET_EPS __uint_as_float(0x358637beu)
@@ -536,7 +536,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
                 const float fMin = fmaxf(pMin, tf);
                 // the children's boxes: parametric interval of the ray inside each (slab test on all three axes; min / max of
                 // the two plane distances per axis orders them whatever the sign of the direction, and drops the NaN of a
-                // zero direction component on a box face), widened by 2^-22 relative so that rounding never culls a box the
+                // zero direction component), widened by the ray's margin (bpad) so that rounding never culls a box the
                 // exact ray touches.  A child the ray misses is never fetched; a child that is entered gets the tighter interval.
                 float bnL, bfL, bnR, bfR;
                 BOX_SLAB(b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, bnL, bfL);

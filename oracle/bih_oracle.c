@@ -512,13 +512,13 @@ static void traverse_proper(const orc_scene* s, const orc_ray* r, orc_hit* rec, 
  * box.  The boxes are exact min / max of vertex coordinates, so the leaves entered are a SUBSET of traverse_proper's, in
  * the same order: a leaf is skipped only when the ray cannot hit a triangle in it before the closest hit so far -- the
  * result equals traverse_proper's (and hence TraverseTree's) except where Moller-Trumbore's rounded t disagrees with a
- * rounded box distance by more than the 2^-22 margin (relative to t and to |o/d|), i.e. on grazing edge / vertex hits (the documented tie
+ * rounded box distance by more than the ray's margin (2^-22 x (largest finite |o/d| + larger end of its scene interval)), i.e. on grazing edge / vertex hits (the documented tie
  * class).  Same arithmetic, operation order and NaN behaviour as the kernel, so GPU results and counters are compared
  * bit for bit against this mode; tests/test_oracle_semantics.py ties it back to traverse_ref. */
 #define BOX_EPS 2.384185791015625e-07f      /* 2^-22 */
 /* plane distance as ONE fused multiply-add: t = fma(plane, 1/d, -(o/d)).  The rounding of o/d is an absolute error of
- * 2^-24 |o/d| in t, so every box interval is widened by pad = 2^-22 x the largest finite |o/d| of the ray, and by 2^-22
- * relative for the rounding of the FMA itself. */
+ * 2^-24 |o/d| in t, so every box interval is widened by pad = 2^-22 x the largest finite |o/d| of the ray, plus 2^-22 x the
+ * larger end of the ray's scene interval for the rounding of the FMA itself (see make_boxray). */
 typedef struct { float inv[3], n[3], pad; } orc_boxray;
 static inline void make_boxray(orc_boxray* q, const orc_ray* r, float sMin, float sMax) {
     float m = 0.0f;
