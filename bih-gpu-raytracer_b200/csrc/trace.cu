@@ -81,6 +81,9 @@
 
 struct Hit { float t; int slot; };
 
+__device__ __forceinline__ float fmin3(float a, float b, float c) { float r; asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
+__device__ __forceinline__ float fmax3(float a, float b, float c) { float r; asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
+
 // Color + rgbToInt, R/src/CUDAKernels.cu:82-88,385-387,420-422: mean over the samples of hit (255,255,0) /
 // miss (20,20,40), packed r | g<<8 | b<<16 (sums of 255/20/40 are exact in binary32)
 __device__ __forceinline__ uint32_t pack_colour(uint32_t hits, int samples) {
@@ -532,8 +535,6 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
                 const float t1 = __fmul_rn(__fsub_rn(nd.y, oi.x), oi.y);
                 const float tn = neg ? t1 : t0, tf = neg ? t0 : t1;
                 const uint32_t refn = neg ? rr : rl, reff = neg ? rl : rr;
-                const float nMax = fminf(pMax, tn);
-                const float fMin = fmaxf(pMin, tf);
                 // the children's boxes: parametric interval of the ray inside each (slab test on all three axes; min / max of
                 // the two plane distances per axis orders them whatever the sign of the direction, and drops the NaN of a
                 // zero direction component), widened by the ray's margin (bpad) so that rounding never culls a box the
@@ -541,8 +542,9 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(Trace
                 float bnL, bfL, bnR, bfR;
                 BOX_SLAB(b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, bnL, bfL);
                 BOX_SLAB(b1.z, b1.w, b2.x, b2.y, b2.z, b2.w, bnR, bfR);
-                const float nLo = fmaxf(pMin, neg ? bnR : bnL), nHi = fminf(nMax, neg ? bfR : bfL);
-                const float fLo = fmaxf(fMin, neg ? bnL : bnR), fHi = fminf(pMax, neg ? bfL : bfR);
+                // (three-input min / max, FMNMX3: same NaN and signed-zero behaviour as the nested two-input calls they replace)
+                const float nLo = fmaxf(pMin, neg ? bnR : bnL), nHi = fmin3(pMax, tn, neg ? bfR : bfL);
+                const float fLo = fmax3(pMin, tf, neg ? bnL : bnR), fHi = fminf(pMax, neg ? bfL : bfR);
                 const bool go_near = (Q || rMin < tn) && (nLo <= nHi);   // reference's strict test (:292) + closed tight interval
                 const bool go_far = (fLo <= fHi);
                 // (the four cases as SELECTS instead of branch targets were measured: 4K x 16 spp 11997 -> 11259 Mrays/s, atrium -9 %:
